@@ -1,0 +1,275 @@
+"""Deterministic synthetic rigs in the reference's dataset conventions.
+
+There is no network, so the reference's sample datasets ("box", "pentagonal", README.md:55-56 of the
+reference) are replaced by seeded generators that emit exactly what the hot path consumes:
+
+* the `Initializer` output the 8-argument `MultiCamMapper` constructor takes
+  (libs/multicam_mapper.h:17): root ids, `map<int,4x4>` of camera->root-camera, marker->root-marker
+  and object(root marker)->root-camera transforms (float32-rounded entries like the IPPE output,
+  libs/initializer.cpp:403-409), camera matrices and distortion coefficients, and the
+  `frame -> cam -> [aruco::Marker]` detections;
+* optionally a dataset folder (`<cam>/calib.yml` + `aruco.detections`).
+
+Everything is numpy; generation is chunked over frames so the 100k-frame config fits in RAM.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import struct
+
+import numpy as np
+
+# BASELINE.json configs: (cameras, markers, frames, target marker observations per frame)
+CONFIGS = {
+    "cfg1": dict(C=3, M=6, F=200, obs_per_frame=6.0),
+    "cfg2": dict(C=5, M=12, F=1000, obs_per_frame=15.0),
+    "cfg3": dict(C=8, M=24, F=10000, obs_per_frame=50.0),
+    "cfg4": dict(C=16, M=64, F=100000, obs_per_frame=256.0),
+    "cfg5": dict(C=16, M=64, F=100000, obs_per_frame=256.0),  # track mode: same density, frames independent
+}
+
+
+@dataclasses.dataclass
+class Rig:
+    cam_ids: np.ndarray        # int32 [C], ascending
+    marker_ids: np.ndarray     # int32 [M], ascending
+    frame_ids: np.ndarray      # int32 [F], ascending (frames with < 2 detections dropped)
+    K: np.ndarray              # float64 [C,3,3]
+    dist: np.ndarray           # float64 [C,5]  k1 k2 p1 p2 k3
+    image_size: tuple
+    marker_size: np.float32
+    root_cam: int
+    root_marker: int
+    T_cam_true: np.ndarray     # [C,4,4] camera -> root camera
+    T_marker_true: np.ndarray  # [M,4,4] marker -> root marker
+    T_frame_true: np.ndarray   # [F,4,4] root marker -> root camera
+    T_cam_init: np.ndarray
+    T_marker_init: np.ndarray
+    T_frame_init: np.ndarray
+    det_frame: np.ndarray      # int32 [N] frame id, file order (frame, cam, detection order)
+    det_cam: np.ndarray        # int32 [N]
+    det_marker: np.ndarray     # int32 [N]
+    det_xy: np.ndarray         # float32 [N,8] x0 y0 x1 y1 x2 y2 x3 y3 (raw, i.e. distorted, pixels)
+
+    @property
+    def C(self): return len(self.cam_ids)
+    @property
+    def M(self): return len(self.marker_ids)
+    @property
+    def F(self): return len(self.frame_ids)
+    @property
+    def N(self): return len(self.det_frame)
+
+
+def rodrigues(r):
+    """(...,3) rotation vectors -> (...,3,3); plain numpy, generator use only."""
+    r = np.asarray(r, dtype=np.float64)
+    th = np.linalg.norm(r, axis=-1)[..., None, None]
+    k = r / np.maximum(np.linalg.norm(r, axis=-1, keepdims=True), 1e-300)
+    Kx = np.zeros(r.shape[:-1] + (3, 3))
+    Kx[..., 0, 1] = -k[..., 2]; Kx[..., 0, 2] = k[..., 1]
+    Kx[..., 1, 0] = k[..., 2]; Kx[..., 1, 2] = -k[..., 0]
+    Kx[..., 2, 0] = -k[..., 1]; Kx[..., 2, 1] = k[..., 0]
+    I = np.broadcast_to(np.eye(3), Kx.shape)
+    kkT = k[..., :, None] * k[..., None, :]
+    return np.cos(th) * I + (1 - np.cos(th)) * kkT + np.sin(th) * Kx
+
+
+def se3(R, t):
+    T = np.zeros(R.shape[:-2] + (4, 4))
+    T[..., :3, :3] = R
+    T[..., :3, 3] = t
+    T[..., 3, 3] = 1.0
+    return T
+
+
+def se3_inv(T):
+    R = T[..., :3, :3]; t = T[..., :3, 3]
+    Rt = np.swapaxes(R, -1, -2)
+    return se3(Rt, -(Rt @ t[..., None])[..., 0])
+
+
+def _look_at(eye, target=np.zeros(3), up=np.array([0.0, 0.0, 1.0])):
+    """camera->world pose with +z looking from eye to target (OpenCV camera axes: x right, y down)."""
+    z = target - eye; z /= np.linalg.norm(z)
+    x = np.cross(z, up); x /= np.linalg.norm(x)
+    y = np.cross(z, x)
+    return se3(np.stack([x, y, z], axis=1), eye)
+
+
+def _fibonacci_sphere(n):
+    i = np.arange(n) + 0.5
+    phi = np.arccos(1 - 2 * i / n)
+    th = np.pi * (1 + 5 ** 0.5) * i
+    return np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+
+
+def _perturb(T, rng, rot_sigma, trans_sigma):
+    n = T.shape[0]
+    dT = se3(rodrigues(rng.normal(0, rot_sigma, (n, 3))), rng.normal(0, trans_sigma, (n, 3)))
+    out = T @ dT
+    out = out.astype(np.float32).astype(np.float64)  # IPPE matrices are CV_32F (initializer.cpp:403-409)
+    out[:, 3, :] = [0, 0, 0, 1]
+    return out
+
+
+def _distort(xn, yn, d):
+    k1, k2, p1, p2, k3 = d
+    r2 = xn * xn + yn * yn
+    rad = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = xn * rad + 2 * p1 * xn * yn + p2 * (r2 + 2 * xn * xn)
+    yd = yn * rad + p1 * (r2 + 2 * yn * yn) + 2 * p2 * xn * yn
+    return xd, yd
+
+
+def make_rig(C, M, F, obs_per_frame, seed=0, marker_size=0.05, noise_px=0.3, distorted=False,
+             rot_sigma=0.02, trans_sigma=0.005, shuffle_detections=True, sparse_marker_ids=True,
+             chunk_frames=2000) -> Rig:
+    rng = np.random.default_rng(seed)
+    W, H = 1280, 720
+    # cameras on a ring of radius 1.5 m looking at the origin (world frame), slightly varied height
+    ang = 2 * np.pi * np.arange(C) / C + rng.normal(0, 0.05, C)
+    eyes = np.stack([1.5 * np.cos(ang), 1.5 * np.sin(ang), rng.uniform(-0.3, 0.5, C)], axis=1)
+    T_cw = np.stack([_look_at(e) for e in eyes])            # camera -> world
+    T_cam_true = se3_inv(T_cw[0:1]) @ T_cw                  # camera -> root camera (cam 0 is root: identity)
+    T_cam_true[0] = np.eye(4)
+    f = 1000.0 * (1 + rng.uniform(-0.02, 0.02, C))
+    K = np.zeros((C, 3, 3)); K[:, 0, 0] = f; K[:, 1, 1] = f; K[:, 0, 2] = 640.0; K[:, 1, 2] = 360.0; K[:, 2, 2] = 1.0
+    dist = np.zeros((C, 5))
+    if distorted:
+        dist[:] = [-0.1, 0.05, 1e-3, -2e-3, 0.01]
+        dist += rng.normal(0, 1e-3, dist.shape) * np.array([10, 5, 0.1, 0.1, 1])
+
+    # markers on a polyhedron of circumradius 0.15 m, outward-facing (object frame)
+    nrm = _fibonacci_sphere(M)
+    Tm_obj = np.zeros((M, 4, 4))
+    for i in range(M):
+        z = nrm[i]
+        a = np.array([0.0, 0.0, 1.0]) if abs(z[2]) < 0.9 else np.array([1.0, 0.0, 0.0])
+        x = np.cross(a, z); x /= np.linalg.norm(x)
+        spin = rng.uniform(0, 2 * np.pi)
+        y = np.cross(z, x)
+        x, y = np.cos(spin) * x + np.sin(spin) * y, -np.sin(spin) * x + np.cos(spin) * y
+        Tm_obj[i] = se3(np.stack([x, y, z], axis=1), 0.15 * z)
+    T_marker_true = se3_inv(Tm_obj[0:1]) @ Tm_obj            # marker -> root marker (marker 0 is root)
+    T_marker_true[0] = np.eye(4)
+    marker_ids = (np.arange(M) * 3 + 7 if sparse_marker_ids else np.arange(M)).astype(np.int32)
+    cam_ids = np.arange(C, dtype=np.int32)
+
+    h = np.float32(marker_size) / np.float32(2)
+    Xm = np.array([[-h, h, 0, 1], [h, h, 0, 1], [h, -h, 0, 1], [-h, -h, 0, 1]], dtype=np.float64).T  # 4x4, columns=corners
+
+    # smooth object trajectory (world frame): low-frequency sinusoids inside a 0.5 m cube, slow tumbling
+    tt = np.arange(F) / max(F, 1)
+    ph = rng.uniform(0, 2 * np.pi, (3, 3)); fr = rng.uniform(0.5, 3.0, (3, 3))
+    pos = 0.25 * np.stack([np.sin(2 * np.pi * fr[0, i] * tt * (1 + F / 2000.0) + ph[0, i]) for i in range(3)], axis=1) * 0.8
+    rv = np.stack([1.2 * np.sin(2 * np.pi * fr[1, i] * tt * (1 + F / 3000.0) + ph[1, i]) + 0.8 * np.sin(2 * np.pi * fr[2, i] * tt * 7 + ph[2, i]) for i in range(3)], axis=1)
+    T_ow = se3(rodrigues(rv), pos)                           # object -> world
+    # root marker -> root camera = inv(T_cw0) * T_ow * Tm_obj0
+    T_frame_all = se3_inv(T_cw[0]) @ T_ow @ Tm_obj[0]
+
+    det_f, det_c, det_m, det_xy = [], [], [], []
+    # estimate visibility rate on the first chunk to set the Bernoulli thinning probability
+    p_keep = None
+    Tci = se3_inv(T_cam_true)                                # root camera -> camera
+    for f0 in range(0, F, chunk_frames):
+        f1 = min(F, f0 + chunk_frames)
+        n = f1 - f0
+        # T[f,c,m] = inv(Tc) * To * Tm   -> (n,C,M,4,4)
+        A = Tci[None, :, None] @ T_frame_all[f0:f1, None, None] @ T_marker_true[None, None, :]
+        P = A[..., :3, :] @ Xm                               # (n,C,M,3,4) camera-frame corner coordinates
+        z = P[..., 2, :]
+        xn = P[..., 0, :] / z; yn = P[..., 1, :] / z
+        if distorted:
+            xd = np.empty_like(xn); yd = np.empty_like(yn)
+            for c in range(C):
+                xd[:, c], yd[:, c] = _distort(xn[:, c], yn[:, c], dist[c])
+        else:
+            xd, yd = xn, yn
+        u = xd * K[None, :, None, None, 0, 0] + K[None, :, None, None, 0, 2]
+        v = yd * K[None, :, None, None, 1, 1] + K[None, :, None, None, 1, 2]
+        normal = A[..., :3, 2]; centre = A[..., :3, 3]
+        view = centre / np.linalg.norm(centre, axis=-1, keepdims=True)
+        facing = (normal * view).sum(-1) < -0.2
+        inside = ((u > 1) & (u < W - 2) & (v > 1) & (v < H - 2) & (z > 0.1)).all(-1)
+        vis = facing & inside
+        if p_keep is None:
+            rate = vis.sum() / max(n, 1)
+            p_keep = min(1.0, obs_per_frame / max(rate, 1e-9))
+        keep = vis & (rng.random(vis.shape) < p_keep)
+        fi, ci, mi = np.nonzero(keep)                        # sorted by (frame, cam, marker)
+        if shuffle_detections and len(fi):
+            # random detection order inside every (frame, cam) group
+            key = rng.random(len(fi))
+            order = np.lexsort((key, ci, fi))
+            fi, ci, mi = fi[order], ci[order], mi[order]
+        xy = np.stack([u[fi, ci, mi], v[fi, ci, mi]], axis=-1)            # (n_obs,4,2)
+        xy = xy + rng.normal(0, noise_px, xy.shape)
+        det_f.append((fi + f0).astype(np.int32)); det_c.append(cam_ids[ci]); det_m.append(marker_ids[mi])
+        det_xy.append(xy.reshape(-1, 8).astype(np.float32))
+    det_f = np.concatenate(det_f); det_c = np.concatenate(det_c); det_m = np.concatenate(det_m); det_xy = np.concatenate(det_xy)
+    # frames with fewer than 2 detections are dropped (initializer.h:53, initializer.cpp:379)
+    cnt = np.bincount(det_f, minlength=F)
+    ok = cnt >= 2
+    sel = ok[det_f]
+    det_f, det_c, det_m, det_xy = det_f[sel], det_c[sel], det_m[sel], det_xy[sel]
+    frame_ids = np.nonzero(ok)[0].astype(np.int32)
+    T_frame_true = T_frame_all[frame_ids]
+
+    T_cam_init = _perturb(T_cam_true, rng, rot_sigma, trans_sigma); T_cam_init[0] = np.eye(4)
+    T_marker_init = _perturb(T_marker_true, rng, rot_sigma, trans_sigma); T_marker_init[0] = np.eye(4)
+    T_frame_init = _perturb(T_frame_true, rng, rot_sigma, trans_sigma)
+    return Rig(cam_ids=cam_ids, marker_ids=marker_ids, frame_ids=frame_ids, K=K, dist=dist, image_size=(W, H),
+               marker_size=np.float32(marker_size), root_cam=int(cam_ids[0]), root_marker=int(marker_ids[0]),
+               T_cam_true=T_cam_true, T_marker_true=T_marker_true, T_frame_true=T_frame_true,
+               T_cam_init=T_cam_init, T_marker_init=T_marker_init, T_frame_init=T_frame_init,
+               det_frame=det_f, det_cam=det_c.astype(np.int32), det_marker=det_m.astype(np.int32), det_xy=det_xy)
+
+
+def make_config(name: str, seed=None, frames=None, **kw) -> Rig:
+    cfg = dict(CONFIGS[name])
+    if frames is not None:
+        cfg["F"] = frames
+    if seed is None:
+        seed = int(name[-1])
+    return make_rig(cfg["C"], cfg["M"], cfg["F"], cfg["obs_per_frame"], seed=seed, **kw)
+
+
+# ------------------------------------------------------------------ dataset files (Appendix A.1/A.2)
+def write_detections_file(path, rig: Rig):
+    """`aruco.detections`: size_t num_cams, then per frame, per cam: size_t n, n x {int id, 8 float}
+    (reader: libs/initializer.cpp:316-362; record: libs/aruco_serdes.cpp:9-24).  The frame index in
+    the file is the ordinal, so every frame up to the last id is written (possibly empty)."""
+    C = rig.C
+    nF = int(rig.frame_ids.max()) + 1 if rig.F else 0
+    order = np.lexsort((np.arange(rig.N), rig.det_cam, rig.det_frame))
+    starts = np.searchsorted(rig.det_frame[order] * C + rig.det_cam[order], np.arange(nF * C + 1))
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<Q", C))
+        for f in range(nF):
+            for c in range(C):
+                a, b = starts[f * C + c], starts[f * C + c + 1]
+                fh.write(struct.pack("<Q", b - a))
+                for k in order[a:b]:
+                    fh.write(struct.pack("<i8f", int(rig.det_marker[k]), *[float(x) for x in rig.det_xy[k]]))
+
+
+def write_calib_files(folder, rig: Rig):
+    """<folder>/<cam>/calib.yml in OpenCV FileStorage YAML (reader: libs/cam_config.cpp:52-78)."""
+    for i, cid in enumerate(rig.cam_ids):
+        d = os.path.join(folder, str(int(cid)))
+        os.makedirs(d, exist_ok=True)
+        Kv = ", ".join(repr(float(x)) for x in rig.K[i].reshape(-1))
+        dv = ", ".join(repr(float(x)) for x in rig.dist[i])
+        with open(os.path.join(d, "calib.yml"), "w") as fh:
+            fh.write("%YAML:1.0\n---\n")
+            fh.write(f"image_width: {rig.image_size[0]}\nimage_height: {rig.image_size[1]}\n")
+            fh.write(f"camera_matrix: !!opencv-matrix\n   rows: 3\n   cols: 3\n   dt: d\n   data: [ {Kv} ]\n")
+            fh.write(f"distortion_coefficients: !!opencv-matrix\n   rows: 1\n   cols: 5\n   dt: d\n   data: [ {dv} ]\n")
+
+
+def write_dataset(folder, rig: Rig):
+    os.makedirs(folder, exist_ok=True)
+    write_calib_files(folder, rig)
+    write_detections_file(os.path.join(folder, "aruco.detections"), rig)
