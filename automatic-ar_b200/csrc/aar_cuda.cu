@@ -1,0 +1,766 @@
+// aar_cuda.cu — C-ABI layer (include/aar_cuda.h) over the sm_100a kernels of aar_kernels.cuh.
+// Host side of the drop-in: problem description -> row/column maps (bit-exact contract), SoA upload,
+// device-resident Levenberg-Marquardt loop, NCCL all-reduce of the reduced system for frame shards.
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h> // types only; the library is dlopen'ed so single-GPU use needs no NCCL
+
+#include "../../include/aar_cuda.h"
+#include "aar_host_math.h"
+#include "aar_kernels.cuh"
+
+using namespace aar;
+
+namespace {
+
+thread_local std::string g_err;
+void set_err(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+}
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) { set_err("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return AAR_ERR_CUDA; } \
+    } while (0)
+
+// ------------------------------------------------------------------------------ NCCL (dlopen)
+struct Nccl {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { set_err("NCCL: cannot dlopen libnccl.so.2: %s", dlerror()); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_err("NCCL: missing symbols"); return false; }
+        return true;
+    }
+} g_nccl;
+
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) { free(); n = count; if (!count) return cudaSuccess; return cudaMalloc((void **)&p, count * sizeof(T)); }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free(); }
+};
+
+} // namespace
+
+struct aar_problem {
+    // ---- description (host)
+    int C = 0, M = 0, F = 0;                      // global counts
+    std::vector<int> cam_ids, marker_ids, frame_ids;
+    int root_cam_id = 0, root_marker_id = 0, root_cam = 0, root_marker = 0;
+    float marker_size = 0;
+    std::vector<double> cam_T, marker_T, frame_T, cam_K, cam_dist;
+    bool opt_c = true, opt_m = true, opt_f = true, huber = false;
+    double J_delta = 1e-3;
+    int device = 0, rank = 0, world = 1;
+    // ---- row map (global, a1 order) and shard
+    long long N = 0;                               // global observations
+    std::vector<int> g_frame, g_cam, g_marker, g_hasjac; // indices per global observation
+    int f_begin = 0, f_end = 0;                    // this rank's frame index range
+    long long o_begin = 0, o_end = 0;              // this rank's observation range
+    int nrc = 0, nrm = 0, n_r = 0;
+    long long n_vars = 0;
+    long long nslots = 0; int max_slots = 0;
+    // ---- device
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
+    DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
+    DevBuf<double> d_intr, d_K9, d_dist5, d_camv, d_mkv, d_frv, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
+    DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
+    DevBuf<LmState> d_st;
+    DevBuf<int> d_flag;
+    LmState *h_st = nullptr; double *h_red3 = nullptr; // pinned
+    DevProblem dp{};
+    // ---- LM host mirror
+    aar_lm_params params{};
+    bool lm_active = false;
+    float huber_cur = 2.5f, huber_eval = 2.5f;
+    double prev_cost = 0, cost = 0, initial_cost = 0;
+    int iter = 0; int exit_code = 0; long long total_tries = 0;
+    // ---- comm
+    ncclComm_t comm = nullptr;
+    // ---- instrumentation
+    long long launches = 0; bool profiling = false;
+    cudaEvent_t ev[8] = {}; double phase_ms[5] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+#define LAUNCH(p, kernel, grid, block, smem, ...)                                    \
+    do { kernel<<<(grid), (block), (smem), (p)->stream>>>(__VA_ARGS__); (p)->launches++; } while (0)
+
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+void pose12_from_T16(const double *T, double *out) {
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) out[i * 3 + j] = T[i * 4 + j]; out[9 + i] = T[i * 4 + 3]; }
+}
+
+bool strictly_ascending(const std::vector<int> &v) { for (size_t i = 1; i < v.size(); i++) if (v[i] <= v[i - 1]) return false; return true; }
+
+int rank_of(const std::vector<int> &ids, int id) {
+    auto it = std::lower_bound(ids.begin(), ids.end(), id);
+    if (it == ids.end() || *it != id) return -1;
+    return (int)(it - ids.begin());
+}
+
+// column of a block in io_vec (multicam_mapper.cpp:815-817, 824-826, 833)
+long long col_cam(const aar_problem *p, int i) { if (!p->opt_c || i == p->root_cam) return -1; return 6LL * (i - (i > p->root_cam ? 1 : 0)); }
+long long col_marker(const aar_problem *p, int j) { if (!p->opt_m || j == p->root_marker) return -1; return 6LL * p->nrc + 6LL * (j - (j > p->root_marker ? 1 : 0)); }
+long long col_frame(const aar_problem *p, int k) { if (!p->opt_f) return -1; return 6LL * (p->nrc + p->nrm) + 6LL * k; }
+
+int allreduce(aar_problem *p, double *buf, size_t n, ncclRedOp_t op) {
+    if (!p->comm) return AAR_OK;
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, n, ncclFloat64, op, p->comm, p->stream);
+    if (r != ncclSuccess) { set_err("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return AAR_ERR_COMM; }
+    return AAR_OK;
+}
+
+// expands z (device) into the pose tables; trial != 0 -> base-only trial tables
+int expand(aar_problem *p, const double *dz, int trial) {
+    const int jobs = p->C * (trial ? 1 : NVAR_CAM) + p->M * (trial ? 1 : NVAR_RT);
+    LAUNCH(p, k_expand_rig, cdiv(jobs, 128), 128, 0, p->dp, dz, trial);
+    const long long fj = (long long)p->dp.F * (trial ? 1 : NVAR_RT);
+    if (fj > 0) LAUNCH(p, k_expand_frames, cdiv(fj, 128), 128, 0, p->dp, dz, trial);
+    return AAR_OK;
+}
+
+// residual sum of squares at dz into d_red3[0] (must be zeroed by the caller); optional residual vector
+int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_out) {
+    expand(p, dz, 1);
+    if (p->dp.N > 0)
+        LAUNCH(p, k_residual, cdiv(p->dp.N, 256), 256, 0, p->dp, p->d_cam_tr.p, POSE_STRIDE, p->d_mk_tr.p, POSE_STRIDE, p->d_fr_tr.p, POSE_STRIDE, huber_delta, d_r_out, p->d_red3.p);
+    return AAR_OK;
+}
+
+constexpr size_t JAC_SMEM = (size_t)144 * JAC_BLOCK * sizeof(double);
+
+int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
+    expand(p, p->d_z.p, 0);
+    if (p->dp.N == 0) return AAR_OK;
+    if (Jdump) LAUNCH(p, k_jacobian<false>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, nullptr, nullptr, nullptr, nullptr, Jdump);
+    else LAUNCH(p, k_jacobian<true>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, nullptr);
+    return AAR_OK;
+}
+
+int zero_normal_equations(aar_problem *p) {
+    if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
+    if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
+    if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
+    if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
+    return AAR_OK;
+}
+
+__global__ void k_prepare_reduced(int n_r, const double *__restrict__ Hrr, const double *__restrict__ gr, double *__restrict__ red) {
+    // red = [S (n_r*n_r) | b (n_r) | Br (n_r)]
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nn = (long long)n_r * n_r;
+    if (e < nn) red[e] = Hrr[e];
+    else if (e < nn + n_r) { double v = -gr[e - nn]; red[e] = v; red[e + n_r] = v; }
+}
+
+size_t schur_smem(const aar_problem *p) { return (size_t)SCHUR_WARPS * std::max(p->max_slots, 1) * 36 * sizeof(double); }
+
+// one try of the do-while of SparseLevMarq::step (sparselevmarq.h:384-419) up to (not including) the decision
+int build_and_solve_reduced(aar_problem *p) {
+    const int n_r = p->n_r;
+    double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
+    if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, S);
+    if (p->opt_f && p->dp.F > 0 && n_r > 0)
+        LAUNCH(p, k_schur, cdiv(p->dp.F, SCHUR_WARPS), SCHUR_WARPS * 32, schur_smem(p), p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, S, b, std::max(p->max_slots, 1), p->d_flag.p);
+    if (n_r > 0) {
+        int rc = allreduce(p, S, (size_t)n_r * n_r + 2 * n_r, ncclSum);
+        if (rc) return rc;
+        LAUNCH(p, k_reduced_solve, 1, 1024, 0, n_r, S, b, p->d_dr.p, p->d_st.p, p->d_flag.p);
+        LAUNCH(p, k_apply_reduced, cdiv(n_r, 128), 128, 0, n_r, p->d_z.p, p->d_dr.p, p->d_zt.p);
+    }
+    (void)Br;
+    return AAR_OK;
+}
+
+int fetch_state(aar_problem *p) {
+    CU(cudaMemcpyAsync(p->h_st, p->d_st.p, sizeof(LmState), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return AAR_OK;
+}
+int push_state(aar_problem *p) {
+    CU(cudaMemcpyAsync(p->d_st.p, p->h_st, sizeof(LmState), cudaMemcpyHostToDevice, p->stream));
+    return AAR_OK;
+}
+
+void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
+
+} // namespace
+
+// ================================================================================ C ABI =====
+extern "C" {
+
+const char *aar_last_error(void) { return g_err.c_str(); }
+
+void aar_lm_default_params(aar_lm_params *q) {
+    q->max_iters = 10000; q->min_error = 1e-5; q->min_step_error_diff = 0; q->min_average_step_error_diff = 1e-4;
+    q->tau = 1; q->der_epsilon = 1e-3; q->ignore_stop_rules = 0; q->verbose = 0;
+}
+
+int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
+    if (!d || !out) { set_err("null argument"); return AAR_ERR_INVALID; }
+    *out = nullptr;
+    if (d->optimize_cam_intrinsics) { set_err("optimize_cam_intrinsics is not supported by the device path (SURVEY 8f row 4)"); return AAR_ERR_UNSUPPORTED; }
+    if (d->num_cams < 1 || d->num_markers < 1 || d->num_frames < 0 || d->num_cams > 4095 || d->num_markers > 500000) { set_err("bad counts"); return AAR_ERR_INVALID; }
+    aar_problem *p = new aar_problem();
+    std::unique_ptr<aar_problem, void (*)(aar_problem *)> guard(p, aar_problem_destroy);
+    p->C = d->num_cams; p->M = d->num_markers; p->F = d->num_frames;
+    p->cam_ids.assign(d->cam_ids, d->cam_ids + p->C);
+    p->marker_ids.assign(d->marker_ids, d->marker_ids + p->M);
+    p->frame_ids.assign(d->frame_ids, d->frame_ids + p->F);
+    if (!strictly_ascending(p->cam_ids) || !strictly_ascending(p->marker_ids) || !strictly_ascending(p->frame_ids)) { set_err("ids must be strictly ascending"); return AAR_ERR_INVALID; }
+    p->root_cam_id = d->root_cam; p->root_marker_id = d->root_marker;
+    p->root_cam = rank_of(p->cam_ids, d->root_cam); p->root_marker = rank_of(p->marker_ids, d->root_marker);
+    if (p->root_cam < 0 || p->root_marker < 0) { set_err("root camera/marker id not among the ids"); return AAR_ERR_INVALID; }
+    p->marker_size = d->marker_size;
+    p->cam_T.assign(d->cam_T, d->cam_T + 16 * (size_t)p->C);
+    p->marker_T.assign(d->marker_T, d->marker_T + 16 * (size_t)p->M);
+    p->frame_T.assign(d->frame_T, d->frame_T + 16 * (size_t)p->F);
+    p->cam_K.assign(d->cam_K, d->cam_K + 9 * (size_t)p->C);
+    p->cam_dist.assign(d->cam_dist, d->cam_dist + 5 * (size_t)p->C);
+    for (int c = 0; c < p->C; c++) {
+        const double *K = &p->cam_K[9 * (size_t)c];
+        if (K[1] != 0 || K[3] != 0 || K[6] != 0 || K[7] != 0 || K[8] != 1) { set_err("camera %d: only [fx 0 cx; 0 fy cy; 0 0 1] camera matrices are supported", p->cam_ids[c]); return AAR_ERR_UNSUPPORTED; }
+    }
+    auto rigid_last_row = [](const std::vector<double> &T) { for (size_t i = 0; i * 16 < T.size(); i++) { const double *r = &T[i * 16 + 12]; if (r[0] != 0 || r[1] != 0 || r[2] != 0 || r[3] != 1) return false; } return true; };
+    if (!rigid_last_row(p->cam_T) || !rigid_last_row(p->marker_T) || !rigid_last_row(p->frame_T)) { set_err("transforms must have last row [0 0 0 1]"); return AAR_ERR_UNSUPPORTED; }
+    p->opt_c = d->optimize_cam_poses; p->opt_m = d->optimize_marker_poses; p->opt_f = d->optimize_object_poses; p->huber = d->with_huber;
+    p->J_delta = d->J_delta > 0 ? d->J_delta : 1e-3;
+    p->device = d->device; p->rank = d->world_size > 1 ? d->rank : 0; p->world = d->world_size > 1 ? d->world_size : 1;
+    if (p->rank < 0 || p->rank >= p->world) { set_err("bad rank"); return AAR_ERR_INVALID; }
+    p->nrc = p->opt_c ? p->C - 1 : 0; p->nrm = p->opt_m ? p->M - 1 : 0; p->n_r = 6 * (p->nrc + p->nrm);
+    p->n_vars = p->n_r + (p->opt_f ? 6LL * p->F : 0);
+
+    // ---- fill_iteration_arrays (multicam_mapper.cpp:345-377): frame id ^, cam id ^, detection order;
+    // detections of unknown cameras / markers are erased.  (Detections of a frame without an object pose make
+    // the reference throw std::out_of_range in project_marker; they are dropped here.)
+    const long long nd = d->num_detections;
+    std::vector<long long> keep; keep.reserve((size_t)nd);
+    std::vector<int> kf((size_t)nd), kc((size_t)nd), km((size_t)nd);
+    for (long long i = 0; i < nd; i++) {
+        int fi = rank_of(p->frame_ids, d->det_frame[i]), ci = rank_of(p->cam_ids, d->det_cam[i]), mi = rank_of(p->marker_ids, d->det_marker[i]);
+        if (fi < 0 || ci < 0 || mi < 0) continue;
+        kf[(size_t)i] = fi; kc[(size_t)i] = ci; km[(size_t)i] = mi; keep.push_back(i);
+    }
+    auto before = [&](long long a, long long b) { return kf[(size_t)a] != kf[(size_t)b] ? kf[(size_t)a] < kf[(size_t)b] : kc[(size_t)a] < kc[(size_t)b]; };
+    if (!std::is_sorted(keep.begin(), keep.end(), before)) // aruco.detections order is already (frame, cam)
+    std::stable_sort(keep.begin(), keep.end(), [&](long long a, long long b) { return kf[(size_t)a] != kf[(size_t)b] ? kf[(size_t)a] < kf[(size_t)b] : kc[(size_t)a] < kc[(size_t)b]; });
+    p->N = (long long)keep.size();
+    p->g_frame.resize((size_t)p->N); p->g_cam.resize((size_t)p->N); p->g_marker.resize((size_t)p->N); p->g_hasjac.assign((size_t)p->N, 1);
+    for (long long o = 0; o < p->N; o++) { long long i = keep[(size_t)o]; p->g_frame[(size_t)o] = kf[(size_t)i]; p->g_cam[(size_t)o] = kc[(size_t)i]; p->g_marker[(size_t)o] = km[(size_t)i]; }
+    // a repeated (frame, cam, marker) overwrites the earlier entry of the inverted indices (:368-370):
+    // only the LAST occurrence contributes Jacobian rows
+    for (long long o = 0; o < p->N;) {
+        long long e = o;
+        while (e < p->N && p->g_frame[(size_t)e] == p->g_frame[(size_t)o] && p->g_cam[(size_t)e] == p->g_cam[(size_t)o]) e++;
+        if (e - o > 1) {
+            std::map<int, long long> last;
+            for (long long q = o; q < e; q++) last[p->g_marker[(size_t)q]] = q;
+            for (long long q = o; q < e; q++) if (last[p->g_marker[(size_t)q]] != q) p->g_hasjac[(size_t)q] = 0;
+        }
+        o = e;
+    }
+    // ---- frame shard: contiguous frame ranges balanced by observation count
+    std::vector<long long> frame_ptr((size_t)p->F + 1, 0);
+    for (long long o = 0; o < p->N; o++) frame_ptr[(size_t)p->g_frame[(size_t)o] + 1]++;
+    for (int f = 0; f < p->F; f++) frame_ptr[(size_t)f + 1] += frame_ptr[(size_t)f];
+    auto boundary = [&](int r) -> int {
+        if (r <= 0) return 0; if (r >= p->world) return p->F;
+        long long target = p->N * r / p->world;
+        int f = (int)(std::lower_bound(frame_ptr.begin(), frame_ptr.end(), target) - frame_ptr.begin());
+        return std::min(f, p->F);
+    };
+    p->f_begin = boundary(p->rank); p->f_end = boundary(p->rank + 1);
+    p->o_begin = frame_ptr[(size_t)p->f_begin]; p->o_end = frame_ptr[(size_t)p->f_end];
+    const int Fl = p->f_end - p->f_begin; const long long Nl = p->o_end - p->o_begin;
+
+    // ---- W slots: per local frame, the distinct active camera / marker blocks seen
+    std::vector<int> slot_ptr((size_t)Fl + 1, 0), slot_block, slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
+    p->max_slots = 0;
+    {
+        std::vector<int> seen((size_t)(p->nrc + p->nrm), -1);
+        for (int f = 0; f < Fl; f++) {
+            const int base = (int)slot_block.size();
+            std::vector<int> touched;
+            for (long long o = frame_ptr[(size_t)(p->f_begin + f)]; o < frame_ptr[(size_t)(p->f_begin + f) + 1]; o++) {
+                if (!p->opt_f) break;
+                const int c = p->g_cam[(size_t)o], m = p->g_marker[(size_t)o];
+                if (p->opt_c && c != p->root_cam) { int b = c - (c > p->root_cam ? 1 : 0); if (seen[(size_t)b] < 0) { seen[(size_t)b] = (int)slot_block.size(); slot_block.push_back(b); touched.push_back(b); } slot_c[(size_t)(o - p->o_begin)] = seen[(size_t)b]; }
+                if (p->opt_m && m != p->root_marker) { int b = p->nrc + m - (m > p->root_marker ? 1 : 0); if (seen[(size_t)b] < 0) { seen[(size_t)b] = (int)slot_block.size(); slot_block.push_back(b); touched.push_back(b); } slot_m[(size_t)(o - p->o_begin)] = seen[(size_t)b]; }
+            }
+            for (int b : touched) seen[(size_t)b] = -1;
+            slot_ptr[(size_t)f + 1] = (int)slot_block.size();
+            p->max_slots = std::max(p->max_slots, (int)slot_block.size() - base);
+        }
+    }
+    p->nslots = (long long)slot_block.size();
+
+    // ---- device
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device: the B200 path has no CPU fallback"); return AAR_ERR_CUDA; }
+    CU(cudaSetDevice(p->device));
+    if (d->stream) p->stream = (cudaStream_t)d->stream; else { CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
+    for (auto &e : p->ev) CU(cudaEventCreate(&e));
+    CU(cudaMallocHost((void **)&p->h_st, sizeof(LmState)));
+    CU(cudaMallocHost((void **)&p->h_red3, 8 * sizeof(double)));
+
+    std::vector<int> obs_f((size_t)Nl), obs_cm((size_t)Nl);
+    std::vector<float4> raw_a((size_t)Nl), raw_b((size_t)Nl);
+    for (long long o = 0; o < Nl; o++) {
+        const long long g = p->o_begin + o, i = keep[(size_t)g];
+        obs_f[(size_t)o] = p->g_frame[(size_t)g] - p->f_begin;
+        obs_cm[(size_t)o] = p->g_cam[(size_t)g] | (p->g_marker[(size_t)g] << 12) | (p->g_hasjac[(size_t)g] ? 0 : (int)0x80000000u);
+        const float *xy = d->det_xy + 8 * i;
+        raw_a[(size_t)o] = make_float4(xy[0], xy[1], xy[2], xy[3]); raw_b[(size_t)o] = make_float4(xy[4], xy[5], xy[6], xy[7]);
+    }
+    std::vector<double> intr(4 * (size_t)p->C), fixed_c(12 * (size_t)p->C), fixed_m(12 * (size_t)p->M), fixed_f(12 * (size_t)std::max(Fl, 1));
+    for (int c = 0; c < p->C; c++) { const double *K = &p->cam_K[9 * (size_t)c]; intr[4 * (size_t)c] = K[0]; intr[4 * (size_t)c + 1] = K[2]; intr[4 * (size_t)c + 2] = K[4]; intr[4 * (size_t)c + 3] = K[5]; pose12_from_T16(&p->cam_T[16 * (size_t)c], &fixed_c[12 * (size_t)c]); }
+    for (int m = 0; m < p->M; m++) pose12_from_T16(&p->marker_T[16 * (size_t)m], &fixed_m[12 * (size_t)m]);
+    for (int f = 0; f < Fl; f++) pose12_from_T16(&p->frame_T[16 * (size_t)(p->f_begin + f)], &fixed_f[12 * (size_t)f]);
+
+#define UP(buf, vec)                                                                                             \
+    do { CU((buf).alloc((vec).size())); if ((vec).size()) CU(cudaMemcpyAsync((buf).p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream)); } while (0)
+    UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
+    UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block);
+    UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
+    UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
+    UP(p->d_cam_fixed, fixed_c); UP(p->d_mk_fixed, fixed_m); UP(p->d_fr_fixed, fixed_f);
+#undef UP
+    CU(p->d_und_a.alloc((size_t)Nl)); CU(p->d_und_b.alloc((size_t)Nl));
+    CU(p->d_camv.alloc((size_t)p->C * NVAR_CAM * POSE_STRIDE)); CU(p->d_mkv.alloc((size_t)p->M * NVAR_RT * POSE_STRIDE)); CU(p->d_frv.alloc((size_t)std::max(Fl, 1) * NVAR_RT * POSE_STRIDE));
+    CU(p->d_cam_tr.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_mk_tr.alloc((size_t)p->M * POSE_STRIDE)); CU(p->d_fr_tr.alloc((size_t)std::max(Fl, 1) * POSE_STRIDE));
+    const size_t nz = (size_t)std::max<long long>(p->n_vars, 1);
+    CU(p->d_z.alloc(nz)); CU(p->d_zt.alloc(nz)); CU(p->d_z0.alloc(nz));
+    CU(p->d_Hf.alloc((size_t)std::max(Fl, 1) * HF_STRIDE)); CU(p->d_W.alloc((size_t)std::max<long long>(p->nslots, 1) * 36));
+    CU(p->d_Hrr.alloc((size_t)std::max(p->n_r, 1) * std::max(p->n_r, 1))); CU(p->d_gr.alloc((size_t)std::max(p->n_r, 1)));
+    CU(p->d_red.alloc((size_t)p->n_r * p->n_r + 2 * (size_t)p->n_r + 8)); CU(p->d_dr.alloc((size_t)std::max(p->n_r, 1)));
+    CU(p->d_red3.alloc(8)); CU(p->d_tmp.alloc((size_t)std::max(p->n_r, 1) + 8)); CU(p->d_st.alloc(1)); CU(p->d_flag.alloc(4));
+    CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
+    CU(cudaMemsetAsync(p->d_st.p, 0, sizeof(LmState), p->stream));
+
+    DevProblem &dp = p->dp;
+    dp.C = p->C; dp.M = p->M; dp.F = Fl; dp.N = Nl; dp.root_cam = p->root_cam; dp.root_marker = p->root_marker;
+    dp.opt_c = p->opt_c; dp.opt_m = p->opt_m; dp.opt_f = p->opt_f; dp.huber = p->huber;
+    dp.nrc = p->nrc; dp.nrm = p->nrm; dp.n_r = p->n_r; dp.col_frame0 = p->n_r + 6 * p->f_begin;
+    dp.h = (double)(p->marker_size / 2.f); // aruco::Marker::get3DPoints: half size in float (marker.cpp:358-369)
+    dp.J_delta = p->J_delta;
+    dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
+    dp.und_a = p->d_und_a.p; dp.und_b = p->d_und_b.p; dp.raw_a = p->d_raw_a.p; dp.raw_b = p->d_raw_b.p;
+    dp.intr = p->d_intr.p; dp.frame_slot_ptr = p->d_frame_slot_ptr.p; dp.slot_block = p->d_slot_block.p;
+    dp.camv = p->d_camv.p; dp.mkv = p->d_mkv.p; dp.frv = p->d_frv.p; dp.cam_tr = p->d_cam_tr.p; dp.mk_tr = p->d_mk_tr.p; dp.fr_tr = p->d_fr_tr.p;
+    dp.cam_fixed = p->d_cam_fixed.p; dp.mk_fixed = p->d_mk_fixed.p; dp.fr_fixed = p->d_fr_fixed.p;
+
+    // ---- remove_distortions (multicam_mapper.cpp:554-578) on the device: raw -> und.
+    // raw_a/raw_b hold corners (0,1) / (2,3); run the point kernel on each half.
+    if (Nl > 0) {
+        // view raw_a as 2*Nl float2 points whose observation is i>>1; reuse k_undistort with a shifted index map:
+        // simplest is a temporary interleaved buffer of 4*Nl points in observation order.
+        DevBuf<float2> tin, tout;
+        CU(tin.alloc(4 * (size_t)Nl)); CU(tout.alloc(4 * (size_t)Nl));
+        std::vector<float2> pts(4 * (size_t)Nl);
+        for (long long o = 0; o < Nl; o++) { const float *xy = d->det_xy + 8 * keep[(size_t)(p->o_begin + o)]; for (int k = 0; k < 4; k++) pts[4 * (size_t)o + k] = make_float2(xy[2 * k], xy[2 * k + 1]); }
+        CU(cudaMemcpyAsync(tin.p, pts.data(), pts.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+        LAUNCH(p, k_undistort, cdiv(4 * Nl, 256), 256, 0, 4 * Nl, tin.p, p->d_obs_cm.p, p->d_K9.p, p->d_dist5.p, tout.p);
+        CU(cudaMemcpyAsync(pts.data(), tout.p, pts.size() * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        std::vector<float4> ua((size_t)Nl), ub((size_t)Nl);
+        for (long long o = 0; o < Nl; o++) { const float2 *q = &pts[4 * (size_t)o]; ua[(size_t)o] = make_float4(q[0].x, q[0].y, q[1].x, q[1].y); ub[(size_t)o] = make_float4(q[2].x, q[2].y, q[3].x, q[3].y); }
+        CU(cudaMemcpyAsync(p->d_und_a.p, ua.data(), ua.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_und_b.p, ub.data(), ub.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+    }
+    CU(cudaFuncSetAttribute(k_jacobian<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM));
+    CU(cudaFuncSetAttribute(k_jacobian<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM));
+    if (schur_smem(p) > 48 * 1024) {
+        if (schur_smem(p) > 227 * 1024) { set_err("frame sees too many blocks for the Schur kernel"); return AAR_ERR_UNSUPPORTED; }
+        CU(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(p)));
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    aar_lm_default_params(&p->params);
+    guard.release();
+    *out = p;
+    return AAR_OK;
+}
+
+void aar_problem_destroy(aar_problem *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->h_st) cudaFreeHost(p->h_st);
+    if (p->h_red3) cudaFreeHost(p->h_red3);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int64_t aar_num_vars(const aar_problem *p) { return p ? p->n_vars : 0; }
+int64_t aar_num_observations(const aar_problem *p) { return p ? p->N : 0; }
+int64_t aar_num_local_observations(const aar_problem *p) { return p ? p->o_end - p->o_begin : 0; }
+int64_t aar_jacobian_nnz(const aar_problem *p) {
+    if (!p) return 0;
+    long long nnz = 0;
+    for (long long o = 0; o < p->N; o++) {
+        if (!p->g_hasjac[(size_t)o]) continue;
+        nnz += 48LL * ((col_cam(p, p->g_cam[(size_t)o]) >= 0) + (col_marker(p, p->g_marker[(size_t)o]) >= 0) + (p->opt_f ? 1 : 0));
+    }
+    return nnz;
+}
+
+int aar_index_maps(const aar_problem *p, int32_t *of, int32_t *oc, int32_t *om, int32_t *oj, int64_t *cc, int64_t *cmk, int64_t *cf, int32_t *fb, int32_t *fe) {
+    if (!p) return AAR_ERR_INVALID;
+    for (long long o = 0; o < p->N; o++) {
+        if (of) of[o] = p->g_frame[(size_t)o];
+        if (oc) oc[o] = p->g_cam[(size_t)o];
+        if (om) om[o] = p->g_marker[(size_t)o];
+        if (oj) oj[o] = p->g_hasjac[(size_t)o];
+    }
+    if (cc) for (int i = 0; i < p->C; i++) cc[i] = col_cam(p, i);
+    if (cmk) for (int j = 0; j < p->M; j++) cmk[j] = col_marker(p, j);
+    if (cf) for (int k = 0; k < p->F; k++) cf[k] = col_frame(p, k);
+    if (fb) *fb = p->f_begin;
+    if (fe) *fe = p->f_end;
+    return AAR_OK;
+}
+
+int aar_get_observations(aar_problem *p, float *und_xy, float *raw_xy) {
+    if (!p) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    const size_t Nl = (size_t)p->dp.N;
+    std::vector<float4> a(Nl), b(Nl);
+    for (int pass = 0; pass < 2; pass++) {
+        float *dst = pass ? raw_xy : und_xy;
+        if (!dst || !Nl) continue;
+        CU(cudaMemcpyAsync(a.data(), pass ? p->d_raw_a.p : p->d_und_a.p, Nl * sizeof(float4), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(b.data(), pass ? p->d_raw_b.p : p->d_und_b.p, Nl * sizeof(float4), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        for (size_t o = 0; o < Nl; o++) { float *q = dst + 8 * o; q[0] = a[o].x; q[1] = a[o].y; q[2] = a[o].z; q[3] = a[o].w; q[4] = b[o].x; q[5] = b[o].y; q[6] = b[o].z; q[7] = b[o].w; }
+    }
+    return AAR_OK;
+}
+
+int aar_mats2evec(const aar_problem *p, double *z) {
+    if (!p || !z) return AAR_ERR_INVALID;
+    size_t vi = 0;
+    auto put = [&](const double *T) {
+        double R[9], rv[3];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i * 3 + j] = T[i * 4 + j];
+        aar_host::rotation_to_vector(R, rv);
+        for (int i = 0; i < 3; i++) { z[vi + i] = rv[i]; z[vi + 3 + i] = T[i * 4 + 3]; }
+        vi += 6;
+    };
+    if (p->opt_c) for (int i = 0; i < p->C; i++) if (i != p->root_cam) put(&p->cam_T[16 * (size_t)i]);
+    if (p->opt_m) for (int i = 0; i < p->M; i++) if (i != p->root_marker) put(&p->marker_T[16 * (size_t)i]);
+    if (p->opt_f) for (int i = 0; i < p->F; i++) put(&p->frame_T[16 * (size_t)i]);
+    return AAR_OK;
+}
+
+static int upload_z(aar_problem *p, const double *z, double *dst) {
+    if (p->n_vars > 0) CU(cudaMemcpyAsync(dst, z, (size_t)p->n_vars * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    return AAR_OK;
+}
+
+int aar_evec2mats(aar_problem *p, const double *z, double *cam_T, double *marker_T, double *frame_T) {
+    if (!p || !z) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    int rc = upload_z(p, z, p->d_zt.p); if (rc) return rc;
+    // trial tables hold the INVERSE camera transform; expand the cameras into a scratch via the marker path instead:
+    // cameras are read back from the Jacobian tables' construction is inverse-only, so re-expand on the fly here.
+    expand(p, p->d_zt.p, 1);
+    std::vector<double> mk(12 * (size_t)p->M), fr(12 * (size_t)std::max(p->dp.F, 1)), ci(12 * (size_t)p->C);
+    CU(cudaMemcpyAsync(mk.data(), p->d_mk_tr.p, mk.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(fr.data(), p->d_fr_tr.p, fr.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(ci.data(), p->d_cam_tr.p, ci.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    auto to16 = [](const double *q, double *T) { for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[i * 4 + j] = q[i * 3 + j]; T[i * 4 + 3] = q[9 + i]; } T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1; };
+    if (marker_T) for (int m = 0; m < p->M; m++) to16(&mk[12 * (size_t)m], marker_T + 16 * (size_t)m);
+    if (frame_T) for (int f = 0; f < p->dp.F; f++) to16(&fr[12 * (size_t)f], frame_T + 16 * (size_t)(p->f_begin + f));
+    if (cam_T) {
+        // camera -> root camera = closed-form rigid inverse of the stored inverse ([R^T | -R^T t]); output-only convenience
+        for (int c = 0; c < p->C; c++) {
+            const double *q = &ci[12 * (size_t)c]; double *T = cam_T + 16 * (size_t)c;
+            for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[i * 4 + j] = q[j * 3 + i]; T[i * 4 + 3] = -(q[0 * 3 + i] * q[9] + q[1 * 3 + i] * q[10] + q[2 * 3 + i] * q[11]); }
+            T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+        }
+    }
+    return AAR_OK;
+}
+
+int aar_eval_residual(aar_problem *p, const double *z, float huber_delta, double *r, double *sum_sq) {
+    if (!p || !z) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    int rc = upload_z(p, z, p->d_zt.p); if (rc) return rc;
+    const size_t nr = 8 * (size_t)p->dp.N;
+    if (r && p->d_r.n < nr) CU(p->d_r.alloc(std::max<size_t>(nr, 8)));
+    CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
+    residual(p, p->d_zt.p, huber_delta, r ? p->d_r.p : nullptr);
+    if (r && nr) CU(cudaMemcpyAsync(r, p->d_r.p, nr * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_red3, p->d_red3.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    if (sum_sq) *sum_sq = p->h_red3[0];
+    return AAR_OK;
+}
+
+int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t *rowidx, double *vals) {
+    if (!p || !z || !colptr || !rowidx || !vals) return AAR_ERR_INVALID;
+    if (p->world != 1) { set_err("aar_eval_jacobian: single-rank handles only"); return AAR_ERR_INVALID; }
+    CU(cudaSetDevice(p->device));
+    int rc = upload_z(p, z, p->d_z.p); if (rc) return rc;
+    const size_t nj = 144 * (size_t)std::max<long long>(p->N, 1);
+    if (p->d_J.n < nj) CU(p->d_J.alloc(nj));
+    jacobian_accumulate(p, p->huber_eval, p->d_J.p);
+    std::vector<double> J(nj);
+    CU(cudaMemcpyAsync(J.data(), p->d_J.p, nj * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    // compressed columns in the order setFromTriplets leaves them: columns ascending, rows ascending
+    std::vector<std::vector<long long>> by_cam((size_t)p->C), by_marker((size_t)p->M), by_frame((size_t)p->F);
+    for (long long o = 0; o < p->N; o++) {
+        if (!p->g_hasjac[(size_t)o]) continue;
+        by_cam[(size_t)p->g_cam[(size_t)o]].push_back(o); by_marker[(size_t)p->g_marker[(size_t)o]].push_back(o); by_frame[(size_t)p->g_frame[(size_t)o]].push_back(o);
+    }
+    long long nnz = 0, col = 0;
+    colptr[0] = 0;
+    auto emit = [&](const std::vector<long long> &obs, int local_col0) {
+        for (int d = 0; d < 6; d++) {
+            for (long long o : obs)
+                for (int q = 0; q < 8; q++) { rowidx[nnz] = (int32_t)(8 * o + q); vals[nnz] = J[(size_t)o * 144 + (size_t)(local_col0 + d) * 8 + q]; nnz++; }
+            colptr[++col] = nnz;
+        }
+    };
+    if (p->opt_c) for (int i = 0; i < p->C; i++) if (i != p->root_cam) emit(by_cam[(size_t)i], 0);
+    if (p->opt_m) for (int i = 0; i < p->M; i++) if (i != p->root_marker) emit(by_marker[(size_t)i], 6);
+    if (p->opt_f) for (int i = 0; i < p->F; i++) emit(by_frame[(size_t)i], 12);
+    return AAR_OK;
+}
+
+int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, double *b, double *cost) {
+    if (!p || !z) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    int rc = upload_z(p, z, p->d_z.p); if (rc) return rc;
+    if ((rc = zero_normal_equations(p))) return rc;
+    CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
+    residual(p, p->d_z.p, p->huber_eval, nullptr);
+    jacobian_accumulate(p, p->huber_eval, nullptr);
+    p->h_st->mu = mu; push_state(p);
+    const int n_r = p->n_r;
+    double *dS = p->d_red.p;
+    if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, dS);
+    if (p->opt_f && p->dp.F > 0 && n_r > 0)
+        LAUNCH(p, k_schur, cdiv(p->dp.F, SCHUR_WARPS), SCHUR_WARPS * 32, schur_smem(p), p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, dS, dS + (size_t)n_r * n_r, std::max(p->max_slots, 1), p->d_flag.p);
+    if (S && n_r) CU(cudaMemcpyAsync(S, dS, (size_t)n_r * n_r * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (b && n_r) CU(cudaMemcpyAsync(b, dS + (size_t)n_r * n_r, (size_t)n_r * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_red3, p->d_red3.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    if (cost) *cost = p->h_red3[0];
+    return AAR_OK;
+}
+
+// ------------------------------------------------------------------------------- LM loop ----
+int aar_lm_begin(aar_problem *p, const double *z0, const aar_lm_params *params) {
+    if (!p || !z0) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    if (params) p->params = *params; else aar_lm_default_params(&p->params);
+    int rc = upload_z(p, z0, p->d_z.p); if (rc) return rc;
+    if (p->n_vars > 0) CU(cudaMemcpyAsync(p->d_z0.p, p->d_z.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    // MultiCamMapper::solve: hubberDelta = 10 before the solver starts (multicam_mapper.cpp:425)
+    p->huber_cur = 10.f; p->huber_eval = 10.f;
+    // SparseLevMarq::init (sparselevmarq.h:237-249)
+    CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
+    residual(p, p->d_z.p, p->huber_cur, nullptr);
+    if ((rc = allreduce(p, p->d_red3.p, 1, ncclSum))) return rc;
+    CU(cudaMemcpyAsync(p->h_red3, p->d_red3.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    std::memset(p->h_st, 0, sizeof(LmState));
+    p->cost = p->prev_cost = p->initial_cost = p->h_red3[0];
+    p->h_st->cost = p->cost; p->h_st->prev_cost = p->prev_cost; p->h_st->mu = -1; p->h_st->v = 2; // v: uninitialised in the reference (sparselevmarq.h:133)
+    if ((rc = push_state(p))) return rc;
+    p->iter = 0; p->exit_code = 0; p->total_tries = 0; p->lm_active = true;
+    if (!std::isfinite(p->cost)) { set_err("initial cost is not finite"); return AAR_ERR_NUMERIC; }
+    return AAR_OK;
+}
+
+int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
+    if (!p || !p->lm_active) { set_err("aar_lm_iterate without aar_lm_begin"); return AAR_ERR_INVALID; }
+    CU(cudaSetDevice(p->device));
+    const aar_lm_params &P = p->params;
+    const int n_r = p->n_r;
+    const long long rows = 8 * p->N;
+    int rc;
+    int done_iters = 0; int mustExit = 0;
+    if (rep) { rep->trace_len = 0; rep->initial_cost = p->initial_cost; }
+    double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
+    for (int it = 0; it < max_iters && !mustExit; it++) {
+        // ---- J, JtJ blocks, B (sparselevmarq.h:353-367)
+        prof_mark(p, 0);
+        if ((rc = zero_normal_equations(p))) return rc;
+        jacobian_accumulate(p, p->huber_eval, nullptr);
+        prof_mark(p, 1);
+        if (p->h_st->mu < 0) { // first iteration: mu = tau * max diag(JtJ) (sparselevmarq.h:369-377)
+            p->h_st->maxdiag = -1e300; push_state(p);
+            if (p->opt_f && p->dp.F > 0) LAUNCH(p, k_maxdiag_frames, cdiv(p->dp.F, 128), 128, 0, p->dp, p->d_Hf.p, p->d_st.p);
+            double *tmp = p->d_tmp.p; // [n_r diag | maxdiag]
+            if (p->comm) {
+                // global diagonal of Hrr (sum) and global frame maximum
+                if (n_r) CU(cudaMemcpy2DAsync(tmp, sizeof(double), p->d_Hrr.p, (size_t)(n_r + 1) * sizeof(double), sizeof(double), (size_t)n_r, cudaMemcpyDeviceToDevice, p->stream));
+                if ((rc = allreduce(p, tmp, (size_t)n_r, ncclSum))) return rc;
+                if ((rc = allreduce(p, &p->d_st.p->maxdiag, 1, ncclMax))) return rc;
+                if ((rc = fetch_state(p))) return rc;
+                LAUNCH(p, k_lm_begin_iter, 1, 1, 0, p->d_st.p, n_r, tmp, 0, P.tau, p->h_st->maxdiag);
+            } else {
+                if ((rc = fetch_state(p))) return rc;
+                LAUNCH(p, k_lm_begin_iter, 1, 1, 0, p->d_st.p, n_r, p->d_Hrr.p, n_r, P.tau, p->h_st->maxdiag);
+            }
+        } else LAUNCH(p, k_lm_begin_iter, 1, 1, 0, p->d_st.p, n_r, p->d_Hrr.p, n_r, P.tau, 0.0);
+        // ---- damping / solve / evaluate / accept-or-reject (sparselevmarq.h:384-419)
+        int ntries = 0; bool accepted = false; double gain = 0;
+        do {
+            CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
+            prof_mark(p, 2);
+            if ((rc = build_and_solve_reduced(p))) return rc;
+            prof_mark(p, 3);
+            if (p->opt_f && p->dp.F > 0) LAUNCH(p, k_backsub, cdiv(p->dp.F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, p->d_dr.p, p->d_z.p, p->d_zt.p, p->d_red3.p);
+            prof_mark(p, 4);
+            residual(p, p->d_zt.p, p->huber_cur, nullptr);
+            prof_mark(p, 5);
+            if ((rc = allreduce(p, p->d_red3.p, 3, ncclSum))) return rc;
+            LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br);
+            if ((rc = fetch_state(p))) return rc;
+            prof_mark(p, 6);
+            CU(cudaGetLastError());
+            p->total_tries++;
+            gain = p->h_st->gain;
+            accepted = p->h_st->accepted != 0;
+            if (accepted) { std::swap(p->d_z.p, p->d_zt.p); p->cost = p->h_st->cost; p->huber_eval = p->huber_cur; }
+            if (p->profiling) {
+                cudaEventSynchronize(p->ev[6]);
+                float ms;
+                if (ntries == 0) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+                cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
+                cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
+                cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->phase_ms[3] += ms;
+                cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]); p->phase_ms[4] += ms;
+            }
+        } while (gain <= 0 && ntries++ < 5 && !accepted);
+        int flags[4];
+        CU(cudaMemcpyAsync(flags, p->d_flag.p, sizeof flags, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        if (!std::isfinite(p->h_st->trial_cost)) { set_err("non-finite cost at iteration %d", p->iter); p->lm_active = false; return AAR_ERR_NUMERIC; }
+        // ---- exit tests of SparseLevMarq::solve (sparselevmarq.h:458-464)
+        const double currErr = p->cost, prevErr = p->prev_cost;
+        if (!P.ignore_stop_rules) {
+            if (currErr < P.min_error) mustExit = 1;
+            if (std::fabs(prevErr - currErr) <= P.min_step_error_diff || std::fabs((prevErr - currErr) / (double)rows) <= P.min_average_step_error_diff || !accepted) mustExit = 2;
+            if (currErr > prevErr) mustExit = 3;
+        }
+        if (P.verbose)
+            printf("Curr Error=%.5g AErr(prev-curr)=%.5g gain=%.5g dumping factor=%.5g\n", currErr, (prevErr - currErr) / (double)rows, gain, p->h_st->mu);
+        if (rep && rep->trace && rep->trace_len < rep->trace_capacity) {
+            aar_lm_trace &t = rep->trace[rep->trace_len++];
+            t.cost = currErr; t.mu = p->h_st->mu; t.gain = gain; t.tries = p->h_st->tries; t.accepted = accepted; t.huber_delta = p->huber_cur;
+        }
+        // step callback: MultiCamMapper::optCallBack (multicam_mapper.cpp:412-417)
+        if (p->huber_cur > 2.5f) p->huber_cur = (float)((double)p->huber_cur - 7.5 / 500);
+        p->prev_cost = currErr;
+        p->h_st->prev_cost = currErr; p->h_st->cost = currErr;
+        if ((rc = push_state(p))) return rc;
+        p->iter++; done_iters++;
+        (void)flags;
+    }
+    p->exit_code = mustExit;
+    if (rep) { rep->final_cost = p->cost; rep->iterations = done_iters; rep->exit_code = mustExit; rep->total_tries = p->total_tries; }
+    return AAR_OK;
+}
+
+int aar_lm_end(aar_problem *p, double *z_out) {
+    if (!p || !p->lm_active) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    if (z_out && p->n_vars > 0) {
+        if (p->comm && p->opt_f) {
+            // every rank owns its frame columns; the reduced part is identical everywhere: zero foreign frames, all-reduce(sum), rank>0 zero their reduced part
+            const size_t fb = (size_t)p->dp.col_frame0, fe = fb + 6 * (size_t)p->dp.F, n = (size_t)p->n_vars;
+            CU(cudaMemcpyAsync(p->d_zt.p, p->d_z.p, n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            if (p->rank != 0 && p->n_r) CU(cudaMemsetAsync(p->d_zt.p, 0, (size_t)p->n_r * sizeof(double), p->stream));
+            if (fb > (size_t)p->n_r) CU(cudaMemsetAsync(p->d_zt.p + p->n_r, 0, (fb - (size_t)p->n_r) * sizeof(double), p->stream));
+            if (fe < n) CU(cudaMemsetAsync(p->d_zt.p + fe, 0, (n - fe) * sizeof(double), p->stream));
+            int rc = allreduce(p, p->d_zt.p, n, ncclSum); if (rc) return rc;
+            CU(cudaMemcpyAsync(z_out, p->d_zt.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        } else CU(cudaMemcpyAsync(z_out, p->d_z.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    p->lm_active = false;
+    return AAR_OK;
+}
+
+int aar_lm_solve(aar_problem *p, double *z, const aar_lm_params *params, aar_lm_report *rep) {
+    int rc = aar_lm_begin(p, z, params); if (rc) return rc;
+    rc = aar_lm_iterate(p, p->params.max_iters, rep); if (rc) return rc;
+    return aar_lm_end(p, z);
+}
+
+int aar_track_batch(aar_problem *, double *, const aar_lm_params *, double *, int32_t *) {
+    set_err("aar_track_batch: not built yet");
+    return AAR_ERR_UNSUPPORTED;
+}
+
+int aar_comm_unique_id(void *id128) {
+    if (!id128) return AAR_ERR_INVALID;
+    if (!g_nccl.load()) return AAR_ERR_COMM;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { set_err("ncclGetUniqueId failed"); return AAR_ERR_COMM; }
+    std::memcpy(id128, &id, sizeof id);
+    return AAR_OK;
+}
+int aar_comm_init(aar_problem *p, const void *id128) {
+    if (!p || !id128) return AAR_ERR_INVALID;
+    if (p->world <= 1) return AAR_OK;
+    if (!g_nccl.load()) return AAR_ERR_COMM;
+    CU(cudaSetDevice(p->device));
+    ncclUniqueId id; std::memcpy(&id, id128, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&p->comm, p->world, id, p->rank);
+    if (r != ncclSuccess) { set_err("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); p->comm = nullptr; return AAR_ERR_COMM; }
+    return AAR_OK;
+}
+
+int64_t aar_kernel_launches(const aar_problem *p) { return p ? p->launches : 0; }
+int aar_set_profiling(aar_problem *p, int32_t on) { if (!p) return AAR_ERR_INVALID; p->profiling = on != 0; for (double &m : p->phase_ms) m = 0; return AAR_OK; }
+int aar_get_phase_ms(const aar_problem *p, double *a, double *b, double *c, double *d, double *e) {
+    if (!p) return AAR_ERR_INVALID;
+    if (a) *a = p->phase_ms[0]; if (b) *b = p->phase_ms[1]; if (c) *c = p->phase_ms[2]; if (d) *d = p->phase_ms[3]; if (e) *e = p->phase_ms[4];
+    return AAR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,615 @@
+// aar_kernels.cuh — sm_100a kernels of the MultiCamMapper / SparseLevMarq hot path.
+// Included once by aar_cuda.cu (single translation unit, compiled with -fmad=false; see
+// aar_device_math.cuh for why).  Reference line numbers are into /root/reference/libs/.
+#pragma once
+#include <cstdint>
+#include "aar_device_math.cuh"
+
+namespace aar {
+
+constexpr int NVAR_CAM = 13;   // inverse camera transform: base + 6 dof x (+,-)
+constexpr int NVAR_RT = 7;     // marker / frame: base + 3 rotation dof x (+,-); translations are perturbed on the fly
+constexpr int POSE_STRIDE = 12;
+
+// Everything the kernels need, by value.
+struct DevProblem {
+    int C, M, F;                 // cameras, markers, LOCAL frames (this rank's shard)
+    long long N;                 // local observations
+    int root_cam, root_marker;   // indices
+    int opt_c, opt_m, opt_f, huber;
+    int nrc, nrm, n_r;           // optimised camera / marker blocks, reduced system size 6*(nrc+nrm)
+    int col_frame0;              // column of this rank's first frame in z
+    double h;                    // half marker size, (float)size/2.f widened
+    double J_delta;
+    // observations, a1 order (frame, cam, detection order)
+    const int *obs_f;            // local frame index
+    const int *obs_cm;           // cam | marker<<12 | nojac<<31
+    const int *obs_slot_c, *obs_slot_m; // W slot of the camera / marker block in this frame, -1 if none
+    const float4 *und_a, *und_b, *raw_a, *raw_b; // x0 y0 x1 y1 | x2 y2 x3 y3
+    const double *intr;          // [C][4] fx cx fy cy
+    // frame CSR
+    const int *frame_slot_ptr;   // [F+1]
+    const int *slot_block;       // [nslots] reduced block index
+    // pose tables
+    double *camv;                // [C][13][12] inverse of camera->root, variants
+    double *mkv;                 // [M][7][12]
+    double *frv;                 // [F][7][12]
+    double *cam_tr, *mk_tr, *fr_tr; // trial (z + delta) tables, base only: [.][12]
+    const double *cam_fixed, *mk_fixed, *fr_fixed; // host matrices [.][12] for non-optimised groups
+};
+
+__device__ __forceinline__ int obs_cam(int cm) { return cm & 0xfff; }
+__device__ __forceinline__ int obs_marker(int cm) { return (cm >> 12) & 0x7ffff; }
+__device__ __forceinline__ bool obs_nojac(int cm) { return cm < 0; }
+
+__device__ __forceinline__ int col_of_cam(const DevProblem &p, int c) { return 6 * (c - (c > p.root_cam ? 1 : 0)); }
+__device__ __forceinline__ int col_of_marker(const DevProblem &p, int m) { return 6 * p.nrc + 6 * (m - (m > p.root_marker ? 1 : 0)); }
+
+__device__ __forceinline__ void store_pose(double *dst, const Pose &p) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) dst[i] = p.r[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) dst[9 + i] = p.t[i];
+}
+
+// vec2transformation_mat (mcm.cpp:463-473) with one component of the rotation vector or of the
+// translation moved by +-delta (obtain_transformation_derivs, mcm.cpp:903-916): variant 0 = base,
+// 1+2d+s = dof d, sign s (0:+, 1:-).
+__device__ __forceinline__ void expand_variant(const double *z6, int variant, double delta, Pose &T) {
+    double rv[3] = {z6[0], z6[1], z6[2]};
+    T.t[0] = z6[3]; T.t[1] = z6[4]; T.t[2] = z6[5];
+    if (variant > 0) {
+        int d = (variant - 1) >> 1;
+        double sg = ((variant - 1) & 1) ? -delta : delta;
+        if (d < 3) rv[d] = rv[d] + sg;
+        else { rodrigues(rv[0], rv[1], rv[2], T.r); T.t[d - 3] = T.t[d - 3] + sg; return; }
+    }
+    rodrigues(rv[0], rv[1], rv[2], T.r);
+}
+
+// cams_vec2mats / markers_vec2mats (mcm.cpp:532-552) + the perturbed copies of
+// obtain_transformation_derivs.  One thread per (entity, variant).  nvar_c/nvar_rt = 1 expands
+// the base only (trial residual), into the *_tr tables when trial != 0.
+__global__ void k_expand_rig(DevProblem p, const double *__restrict__ z, int trial) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nvc = trial ? 1 : NVAR_CAM, nvm = trial ? 1 : NVAR_RT;
+    const int ncam_jobs = p.C * nvc;
+    if (t < ncam_jobs) {
+        int c = t / nvc, v = t % nvc;
+        double *dst = trial ? p.cam_tr + (size_t)c * POSE_STRIDE : p.camv + ((size_t)c * NVAR_CAM + v) * POSE_STRIDE;
+        Pose T, Ti;
+        if (c == p.root_cam) { if (v == 0) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; } return; }
+        if (p.opt_c) expand_variant(z + col_of_cam(p, c), v, p.J_delta, T);
+        else { if (v > 0) return; load_pose(T, p.cam_fixed + (size_t)c * POSE_STRIDE); }
+        inv_rigid_lu(T, Ti);
+        store_pose(dst, Ti);
+        return;
+    }
+    t -= ncam_jobs;
+    if (t < p.M * nvm) {
+        int m = t / nvm, v = t % nvm;
+        double *dst = trial ? p.mk_tr + (size_t)m * POSE_STRIDE : p.mkv + ((size_t)m * NVAR_RT + v) * POSE_STRIDE;
+        Pose T;
+        if (m == p.root_marker) { if (v == 0) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; } return; }
+        if (p.opt_m) expand_variant(z + col_of_marker(p, m), v, p.J_delta, T);
+        else { if (v > 0) return; load_pose(T, p.mk_fixed + (size_t)m * POSE_STRIDE); }
+        store_pose(dst, T);
+    }
+}
+
+// object_poses_vec2mats (mcm.cpp:524-530) + perturbed rotations.
+__global__ void k_expand_frames(DevProblem p, const double *__restrict__ z, int trial) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nv = trial ? 1 : NVAR_RT;
+    if (t >= (long long)p.F * nv) return;
+    int f = (int)(t / nv), v = (int)(t % nv);
+    double *dst = trial ? p.fr_tr + (size_t)f * POSE_STRIDE : p.frv + ((size_t)f * NVAR_RT + v) * POSE_STRIDE;
+    Pose T;
+    if (p.opt_f) expand_variant(z + p.col_frame0 + 6 * (size_t)f, v, p.J_delta, T);
+    else { if (v > 0) return; load_pose(T, p.fr_fixed + (size_t)f * POSE_STRIDE); }
+    store_pose(dst, T);
+}
+
+struct ObsCtx {
+    int f, c, m; bool cam_root, mk_root, nojac;
+    Intr k;
+};
+
+// T1 = inv(Tc) * To (skipped for the root camera, mcm.cpp:617-621)
+__device__ __forceinline__ void make_T1(bool cam_root, const Pose &ci, const Pose &To, Pose &T1) {
+    if (cam_root) { T1 = To; return; }
+    compose_R(ci.r, To.r, T1.r);
+    compose_t(ci.r, ci.t, To.t, T1.t);
+}
+// project T1 * Tm (Tm skipped for the root marker, mcm.cpp:624-628)
+__device__ __forceinline__ void project_T1_Tm(const Pose &T1, bool mk_root, const Pose &Tm, const Intr &k, double h, float *out) {
+    double c0[3], c1[3], t[3];
+    if (mk_root) {
+        c0[0] = T1.r[0]; c0[1] = T1.r[3]; c0[2] = T1.r[6];
+        c1[0] = T1.r[1]; c1[1] = T1.r[4]; c1[2] = T1.r[7];
+        t[0] = T1.t[0]; t[1] = T1.t[1]; t[2] = T1.t[2];
+    } else {
+        compose_R01(T1.r, Tm.r, c0, c1);
+        compose_t(T1.r, T1.t, Tm.t, t);
+    }
+    project(c0, c1, t, k, h, out);
+}
+
+__device__ __forceinline__ void load8(const float4 *a, const float4 *b, long long o, float *x) {
+    float4 u = a[o], v = b[o];
+    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+}
+
+// eval_curr_solution (mcm.cpp:996-1028): residuals of every observation + sum of squares.
+// cam/mk/fr: base pose tables with the given strides (trial tables or variant-0 of the Jacobian tables).
+__global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam_stride, const double *__restrict__ mk, int mk_stride,
+                           const double *__restrict__ fr, int fr_stride, float huber_delta, double *__restrict__ r_out, double *__restrict__ cost) {
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0;
+    if (o < p.N) {
+        int cm = p.obs_cm[o], f = p.obs_f[o], c = obs_cam(cm), m = obs_marker(cm);
+        Intr k; k.fx = p.intr[4 * c]; k.cx = p.intr[4 * c + 1]; k.fy = p.intr[4 * c + 2]; k.cy = p.intr[4 * c + 3];
+        Pose ci, To, Tm, T1;
+        load_pose(To, fr + (size_t)f * fr_stride);
+        bool cam_root = c == p.root_cam, mk_root = m == p.root_marker;
+        if (!cam_root) load_pose(ci, cam + (size_t)c * cam_stride);
+        if (!mk_root) load_pose(Tm, mk + (size_t)m * mk_stride);
+        make_T1(cam_root, ci, To, T1);
+        float pr[8], und[8];
+        project_T1_Tm(T1, mk_root, Tm, k, p.h, pr);
+        load8(p.und_a, p.und_b, o, und);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double ex = (double)(und[2 * i] - pr[2 * i]);       // float - float, widened afterwards (mcm.cpp:1012-1013)
+            double ey = (double)(und[2 * i + 1] - pr[2 * i + 1]);
+            if (p.huber) { double w = huber_weight(ex * ex + ey * ey, huber_delta); ex = w * ex; ey = w * ey; }
+            if (r_out) { r_out[8 * o + 2 * i] = ex; r_out[8 * o + 2 * i + 1] = ey; }
+            acc = fma(ex, ex, acc); acc = fma(ey, ey, acc);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    __shared__ double wsum[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = lane < (blockDim.x >> 5) ? wsum[lane] : 0.0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) atomicAdd(cost, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// jacobian_function (mcm.cpp:739-994) fused with the normal-equation assembly of
+// SparseLevMarq::step (sparselevmarq.h:353-367): J is never materialised.
+// One thread per marker observation.  The 8x18 block [Jc | Jm | Jf] is staged in shared memory
+// (column-major per thread, stride = blockDim so that the accesses are conflict free), then the
+// block products are accumulated:
+//   Hf[f]   += Jf^T Jf (21, upper packed) , gf[f] += Jf^T r
+//   W[slot] += Jc^T Jf / Jm^T Jf (6x6, row = reduced dof)
+//   Hrr     += Jc^T Jc, Jm^T Jm, Jc^T Jm ; gr += Jc^T r, Jm^T r
+// Jdump != nullptr additionally writes the dense per-observation block (parity hook for small problems).
+constexpr int JAC_BLOCK = 128;
+constexpr int HF_STRIDE = 27; // 21 + 6
+
+template <bool ACCUM>
+__global__ void __launch_bounds__(JAC_BLOCK) k_jacobian(DevProblem p, float huber_delta, double *__restrict__ Hf, double *__restrict__ W,
+                                                       double *__restrict__ Hrr, double *__restrict__ gr, double *__restrict__ Jdump) {
+    extern __shared__ double sJ[]; // [18*8][JAC_BLOCK]
+    const int tid = threadIdx.x;
+    long long o = (long long)blockIdx.x * JAC_BLOCK + tid;
+    if (o >= p.N) return;
+    const int cm = p.obs_cm[o], f = p.obs_f[o], c = obs_cam(cm), m = obs_marker(cm);
+    const bool cam_root = c == p.root_cam, mk_root = m == p.root_marker, nojac = obs_nojac(cm);
+    const bool act_c = p.opt_c && !cam_root, act_m = p.opt_m && !mk_root, act_f = p.opt_f != 0;
+    Intr k; k.fx = p.intr[4 * c]; k.cx = p.intr[4 * c + 1]; k.fy = p.intr[4 * c + 2]; k.cy = p.intr[4 * c + 3];
+    const double h = p.h, delta = p.J_delta, two_delta = 2 * p.J_delta;
+    const double *camv = p.camv + (size_t)c * NVAR_CAM * POSE_STRIDE;
+    const double *mkv = p.mkv + (size_t)m * NVAR_RT * POSE_STRIDE;
+    const double *frv = p.frv + (size_t)f * NVAR_RT * POSE_STRIDE;
+    float raw[8], und[8];
+    load8(p.raw_a, p.raw_b, o, raw);
+    load8(p.und_a, p.und_b, o, und);
+
+    Pose ci0, To0, Tm0, T1_0;
+    load_pose(To0, frv);
+    if (!cam_root) load_pose(ci0, camv);
+    if (!mk_root) load_pose(Tm0, mkv);
+    make_T1(cam_root, ci0, To0, T1_0);
+    // residual at z (mcm.cpp:1011-1023)
+    double r[8];
+    {
+        float pr[8];
+        project_T1_Tm(T1_0, mk_root, Tm0, k, h, pr);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double ex = (double)(und[2 * i] - pr[2 * i]), ey = (double)(und[2 * i + 1] - pr[2 * i + 1]);
+            if (p.huber) { double w = huber_weight(ex * ex + ey * ey, huber_delta); ex = w * ex; ey = w * ey; }
+            r[2 * i] = ex; r[2 * i + 1] = ey;
+        }
+    }
+    // obtain_marker_derivs (mcm.cpp:976-994): (float(m - p+) - float(m - p-)) / (2 delta), m = RAW corner
+    auto put_col = [&](int col, const float *pa, const float *ps) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            double ea = (double)(raw[q] - pa[q]), es = (double)(raw[q] - ps[q]);
+            sJ[(col * 8 + q) * JAC_BLOCK + tid] = nojac ? 0.0 : (ea - es) / two_delta;
+        }
+    };
+    float pa[8], ps[8];
+    // --- camera block: the perturbed matrix is inverted (precomputed per camera), then the whole chain is redone
+    if (act_c) {
+        for (int d = 0; d < 6; d++) {
+            Pose civ, T1;
+            load_pose(civ, camv + (size_t)(1 + 2 * d) * POSE_STRIDE);
+            make_T1(false, civ, To0, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, pa);
+            load_pose(civ, camv + (size_t)(2 + 2 * d) * POSE_STRIDE);
+            make_T1(false, civ, To0, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, ps);
+            put_col(d, pa, ps);
+        }
+    }
+    // --- marker block
+    if (act_m) {
+        for (int d = 0; d < 6; d++) {
+            Pose Tv = Tm0;
+            if (d < 3) {
+                for (int i = 0; i < 9; i++) Tv.r[i] = mkv[(size_t)(1 + 2 * d) * POSE_STRIDE + i];
+                project_T1_Tm(T1_0, false, Tv, k, h, pa);
+                for (int i = 0; i < 9; i++) Tv.r[i] = mkv[(size_t)(2 + 2 * d) * POSE_STRIDE + i];
+                project_T1_Tm(T1_0, false, Tv, k, h, ps);
+            } else {
+                Tv.t[d - 3] = Tm0.t[d - 3] + delta; project_T1_Tm(T1_0, false, Tv, k, h, pa);
+                Tv.t[d - 3] = Tm0.t[d - 3] - delta; project_T1_Tm(T1_0, false, Tv, k, h, ps);
+            }
+            put_col(6 + d, pa, ps);
+        }
+    }
+    // --- frame (object pose) block
+    if (act_f) {
+        for (int d = 0; d < 6; d++) {
+            Pose Tv = To0, T1;
+            if (d < 3) {
+                for (int i = 0; i < 9; i++) Tv.r[i] = frv[(size_t)(1 + 2 * d) * POSE_STRIDE + i];
+                make_T1(cam_root, ci0, Tv, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, pa);
+                for (int i = 0; i < 9; i++) Tv.r[i] = frv[(size_t)(2 + 2 * d) * POSE_STRIDE + i];
+                make_T1(cam_root, ci0, Tv, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, ps);
+            } else {
+                Tv.t[d - 3] = To0.t[d - 3] + delta; make_T1(cam_root, ci0, Tv, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, pa);
+                Tv.t[d - 3] = To0.t[d - 3] - delta; make_T1(cam_root, ci0, Tv, T1); project_T1_Tm(T1, mk_root, Tm0, k, h, ps);
+            }
+            put_col(12 + d, pa, ps);
+        }
+    }
+    auto Jv = [&](int col, int q) -> double { return sJ[(col * 8 + q) * JAC_BLOCK + tid]; };
+    if (Jdump) {
+        double *dst = Jdump + (size_t)o * 144;
+        for (int col = 0; col < 18; col++) {
+            bool act = col < 6 ? act_c : (col < 12 ? act_m : act_f);
+            for (int q = 0; q < 8; q++) dst[col * 8 + q] = act ? Jv(col, q) : 0.0;
+        }
+    }
+    if (!ACCUM || nojac) return;
+    // ------------------------------------------------------------------ block products (FMA allowed: sums
+    // of products are not bit-pinned; the reference accumulates them in its own order, sparselevmarq.h:264-325)
+    auto dot = [&](int ca, int cb) -> double {
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s = fma(Jv(ca, q), Jv(cb, q), s);
+        return s;
+    };
+    auto dotr = [&](int ca) -> double {
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s = fma(Jv(ca, q), r[q], s);
+        return s;
+    };
+    const int bc = act_c ? col_of_cam(p, c) : -1, bm = act_m ? col_of_marker(p, m) : -1;
+    const int n_r = p.n_r;
+    if (act_f) {
+        double *hf = Hf + (size_t)f * HF_STRIDE;
+        int idx = 0;
+        for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++) atomicAdd(hf + idx++, dot(12 + i, 12 + j));
+        for (int i = 0; i < 6; i++) atomicAdd(hf + 21 + i, dotr(12 + i));
+        if (act_c) { double *w = W + (size_t)p.obs_slot_c[o] * 36; for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) atomicAdd(w + i * 6 + j, dot(i, 12 + j)); }
+        if (act_m) { double *w = W + (size_t)p.obs_slot_m[o] * 36; for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) atomicAdd(w + i * 6 + j, dot(6 + i, 12 + j)); }
+    }
+    if (act_c) {
+        for (int i = 0; i < 6; i++) {
+            for (int j = i; j < 6; j++) { double v = dot(i, j); atomicAdd(Hrr + (size_t)(bc + i) * n_r + bc + j, v); if (j != i) atomicAdd(Hrr + (size_t)(bc + j) * n_r + bc + i, v); }
+            atomicAdd(gr + bc + i, dotr(i));
+        }
+    }
+    if (act_m) {
+        for (int i = 0; i < 6; i++) {
+            for (int j = i; j < 6; j++) { double v = dot(6 + i, 6 + j); atomicAdd(Hrr + (size_t)(bm + i) * n_r + bm + j, v); if (j != i) atomicAdd(Hrr + (size_t)(bm + j) * n_r + bm + i, v); }
+            atomicAdd(gr + bm + i, dotr(6 + i));
+        }
+    }
+    if (act_c && act_m)
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) atomicAdd(Hrr + (size_t)(bc + i) * n_r + bm + j, dot(i, 6 + j));
+}
+
+// ---------------------------------------------------------------------------------------------
+// LM state, device resident (sparselevmarq.h:130-135, 237-249).
+struct LmState {
+    double cost, prev_cost, trial_cost, mu, v, gain, L;
+    double maxdiag;          // local max diagonal of JtJ (first iteration)
+    float huber_delta, huber_eval;
+    int accepted, tries, iter, exit_code, chol_fail, pad;
+};
+
+// 6x6 Cholesky of packed-upper H + mu I, lower factor L (row-major 6x6, only i>=j used). Returns false on a non-positive pivot.
+__device__ __forceinline__ bool chol6(const double *hf, double mu, double *L) {
+    double A[36];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) { double v = hf[idx++]; A[i * 6 + j] = v; A[j * 6 + i] = v; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) A[i * 6 + i] += mu;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = A[j * 6 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d = fma(-L[j * 6 + k], L[j * 6 + k], d);
+        if (!(d > 0)) { ok = false; d = 1; }
+        d = sqrt(d);
+        L[j * 6 + j] = d;
+        double inv = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double s = A[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s = fma(-L[i * 6 + k], L[j * 6 + k], s);
+            L[i * 6 + j] = s * inv;
+        }
+    }
+    return ok;
+}
+// x <- L^-1 x
+__device__ __forceinline__ void fwd6(const double *L, double *x) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = x[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s = fma(-L[i * 6 + k], x[k], s);
+        x[i] = s / L[i * 6 + i];
+    }
+}
+// x <- L^-T x
+__device__ __forceinline__ void bwd6(const double *L, double *x) {
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double s = x[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s = fma(-L[k * 6 + i], x[k], s);
+        x[i] = s / L[i * 6 + i];
+    }
+}
+
+// Schur elimination of the frame blocks (replaces the sparse LDLT of sparselevmarq.h:394-400 on the
+// arrow-shaped JtJ): one warp per frame.
+//   D = Hff + mu I = L L^T ; E_s = W_s L^-T ; y = L^-1 Bf (Bf = -gf)
+//   S[bs,bt] -= E_s E_t^T (upper block triangle) ; b[bs] -= E_s y
+// S must hold Hrr (without mu) on entry, b must hold Br = -gr.
+constexpr int SCHUR_WARPS = 4;
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevProblem p, const LmState *__restrict__ st, const double *__restrict__ Hf, const double *__restrict__ W,
+                                                            double *__restrict__ S, double *__restrict__ b, int max_slots, int *__restrict__ chol_fail) {
+    extern __shared__ double sE[]; // [SCHUR_WARPS][max_slots][36]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.x * SCHUR_WARPS + wid;
+    if (f >= p.F) return;
+    const double mu = st->mu;
+    double L[36];
+    if (!chol6(Hf + (size_t)f * HF_STRIDE, mu, L) && lane == 0) atomicExch(chol_fail, 1);
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = -Hf[(size_t)f * HF_STRIDE + 21 + i];
+    fwd6(L, y);
+    const int s0 = p.frame_slot_ptr[f], ns = p.frame_slot_ptr[f + 1] - s0;
+    double *E = sE + (size_t)wid * max_slots * 36;
+    const int n_r = p.n_r;
+    for (int s = lane; s < ns; s += 32) {
+        const double *w = W + (size_t)(s0 + s) * 36;
+        const int bs = 6 * p.slot_block[s0 + s];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            double row[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) row[k] = w[i * 6 + k];
+            fwd6(L, row); // e^T = L^-1 w^T
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { E[s * 36 + i * 6 + k] = row[k]; acc = fma(row[k], y[k], acc); }
+            atomicAdd(b + bs + i, -acc);
+        }
+    }
+    __syncwarp();
+    const int npairs = ns * (ns + 1) / 2;
+    for (int q = lane; q < npairs; q += 32) {
+        // unrank q -> (s <= t)
+        int s = 0, rem = q;
+        while (rem >= ns - s) { rem -= ns - s; s++; }
+        int t = s + rem;
+        int bs = 6 * p.slot_block[s0 + s], bt = 6 * p.slot_block[s0 + t];
+        const double *Es = E + s * 36, *Et = E + t * 36;
+        if (bs > bt) { int tmp = bs; bs = bt; bt = tmp; const double *tp = Es; Es = Et; Et = tp; }
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) acc = fma(Es[i * 6 + k], Et[j * 6 + k], acc);
+                atomicAdd(S + (size_t)(bs + i) * n_r + bt + j, -acc);
+            }
+    }
+}
+
+// Dense Cholesky solve of the reduced system (S + mu I) x = b, one CTA, upper triangle of S is valid.
+// Works in place in global memory (S is overwritten with the factor). n_r <= a few hundred.
+__global__ void __launch_bounds__(1024) k_reduced_solve(int n, double *__restrict__ S, const double *__restrict__ b, double *__restrict__ x, const LmState *__restrict__ st, int *__restrict__ chol_fail) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double mu = st->mu;
+    __shared__ double sdiag;
+    // symmetrise: copy upper to lower, add mu
+    for (int e = tid; e < n * n; e += nt) { int i = e / n, j = e % n; if (i > j) S[e] = S[(size_t)j * n + i]; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) S[(size_t)i * n + i] += mu;
+    __syncthreads();
+    // right-looking Cholesky, lower factor stored in the lower triangle
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) { double d = S[(size_t)j * n + j]; if (!(d > 0)) { atomicExch(chol_fail, 1); d = 1; } sdiag = sqrt(d); S[(size_t)j * n + j] = sdiag; }
+        __syncthreads();
+        const double inv = 1.0 / sdiag;
+        for (int i = j + 1 + tid; i < n; i += nt) S[(size_t)i * n + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: S[i][k] -= L[i][j]*L[k][j], j < k <= i
+        const int rem = n - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) S[(size_t)i * n + k] = fma(-S[(size_t)i * n + j], S[(size_t)k * n + j], S[(size_t)i * n + k]);
+        }
+        __syncthreads();
+    }
+    // forward / backward substitution (single warp, serial over rows, parallel dot products)
+    for (int i = tid; i < n; i += nt) x[i] = b[i];
+    __syncthreads();
+    if (tid < 32) {
+        for (int i = 0; i < n; i++) {
+            double s = 0;
+            for (int k = tid; k < i; k += 32) s = fma(S[(size_t)i * n + k], x[k], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
+            __syncwarp();
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double s = 0;
+            for (int k = i + 1 + tid; k < n; k += 32) s = fma(S[(size_t)k * n + i], x[k], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
+            __syncwarp();
+        }
+    }
+}
+
+// Back-substitution delta_f = D^-1 (Bf - W_f^T delta_r) (one thread per frame), trial point z + delta,
+// and the frame part of the two dot products needed by L = 1/2 delta^T (mu delta - B) (sparselevmarq.h:406).
+__global__ void k_backsub(DevProblem p, const LmState *__restrict__ st, const double *__restrict__ Hf, const double *__restrict__ W, const double *__restrict__ dr,
+                          const double *__restrict__ z, double *__restrict__ zt, double *__restrict__ red3) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    double dd = 0, dB = 0;
+    if (f < p.F) {
+        double L[36], rhs[6], B[6];
+        chol6(Hf + (size_t)f * HF_STRIDE, st->mu, L);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { B[i] = -Hf[(size_t)f * HF_STRIDE + 21 + i]; rhs[i] = B[i]; }
+        const int s0 = p.frame_slot_ptr[f], s1 = p.frame_slot_ptr[f + 1];
+        for (int s = s0; s < s1; s++) {
+            const double *w = W + (size_t)s * 36;
+            const double *d = dr + 6 * p.slot_block[s];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int k = 0; k < 6; k++) rhs[k] = fma(-w[i * 6 + k], d[i], rhs[k]);
+        }
+        fwd6(L, rhs); bwd6(L, rhs);
+        const size_t col = (size_t)p.col_frame0 + 6 * (size_t)f;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { zt[col + i] = z[col + i] + rhs[i]; dd = fma(rhs[i], rhs[i], dd); dB = fma(rhs[i], B[i], dB); }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { dd += __shfl_xor_sync(0xffffffffu, dd, s); dB += __shfl_xor_sync(0xffffffffu, dB, s); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(red3 + 1, dd); atomicAdd(red3 + 2, dB); }
+}
+
+// z_trial (reduced part) = z + delta_r
+__global__ void k_apply_reduced(int n_r, const double *__restrict__ z, const double *__restrict__ dr, double *__restrict__ zt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_r) zt[i] = z[i] + dr[i];
+}
+
+// max diagonal of JtJ (sparselevmarq.h:369-377): frames part, local
+__global__ void k_maxdiag_frames(DevProblem p, const double *__restrict__ Hf, LmState *st) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = -DBL_MAX;
+    if (f < p.F) { const int di[6] = {0, 6, 11, 15, 18, 20}; for (int i = 0; i < 6; i++) m = fmax(m, Hf[(size_t)f * HF_STRIDE + di[i]]); }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) {
+        // atomic max on a double via CAS
+        unsigned long long *addr = (unsigned long long *)&st->maxdiag;
+        unsigned long long old = *addr;
+        while (__longlong_as_double((long long)old) < m) {
+            unsigned long long assumed = old;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(m));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// One-thread control kernels -----------------------------------------------------------------
+// after the (all-reduced) normal equations of a new iteration are available
+__global__ void k_lm_begin_iter(LmState *st, int n_r, const double *__restrict__ Hrr_diag_src, int ld, double tau, double frames_maxdiag_global) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (st->mu < 0) { // first time only (sparselevmarq.h:369-377)
+        double m = frames_maxdiag_global;
+        for (int i = 0; i < n_r; i++) m = fmax(m, Hrr_diag_src[(size_t)i * ld + i]);
+        st->mu = m * tau;
+    }
+    st->tries = 0; st->accepted = 0; st->gain = 0;
+}
+// gain / accept / reject (sparselevmarq.h:402-419). red = [trial_cost, dd_f, dB_f] (all-reduced);
+// delta_r.delta_r and delta_r.Br are added here (identical on every rank).
+__global__ void k_lm_decide(LmState *st, const double *__restrict__ red, int n_r, const double *__restrict__ dr, const double *__restrict__ Br) {
+    if (threadIdx.x || blockIdx.x) return;
+    double dd = red[1], dB = red[2];
+    for (int i = 0; i < n_r; i++) { dd = fma(dr[i], dr[i], dd); dB = fma(dr[i], Br[i], dB); }
+    const double err = red[0], mu = st->mu;
+    const double L = 0.5 * (mu * dd - dB);
+    const double gain = (err - st->prev_cost) / L;
+    st->L = L; st->gain = gain; st->trial_cost = err;
+    if (gain > 0 && ((err - st->prev_cost) < 0)) {
+        double t = 2 * gain - 1;
+        st->mu = mu * fmax(0.33, 1. - t * t * t);
+        st->v = 2.;
+        st->cost = err;
+        st->accepted = 1;
+    } else { st->mu = mu * st->v; st->v = st->v * 5; }
+    st->tries += 1;
+}
+
+// one-off device undistortion pass — cv::undistortPoints(..., K, dist, noArray, K) as called by
+// remove_distortions (mcm.cpp:554-578): 5 fixed-point iterations in double, float32 in/out.
+__global__ void k_undistort(long long n4, const float2 *__restrict__ in, const int *__restrict__ obs_cm, const double *__restrict__ K9, const double *__restrict__ dist5, float2 *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c = obs_cam(obs_cm[i >> 2]);
+    const double *K = K9 + 9 * (size_t)c, *k = dist5 + 5 * (size_t)c;
+    const double fx = K[0], fy = K[4], ifx = 1. / fx, ify = 1. / fy, cx = K[2], cy = K[5];
+    float2 uv = in[i];
+    double x = uv.x, y = uv.y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        double r2 = x * x + y * y;
+        double icdist = 1 / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = ((double)uv.x - cx) * ifx; y = ((double)uv.y - cy) * ify; break; }
+        double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+        double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    // RR = K * I : the products with the zeros of K and I vanish exactly; ww = 1/(0*x + 0*y + 1) = 1
+    double xx = K[0] * x + K[1] * y + K[2];
+    double yy = K[3] * x + K[4] * y + K[5];
+    double ww = 1. / (K[6] * x + K[7] * y + K[8]);
+    out[i] = make_float2((float)(xx * ww), (float)(yy * ww));
+}
+
+} // namespace aar

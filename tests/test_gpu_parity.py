@@ -1,0 +1,168 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path behind the C ABI (include/aar_cuda.h)
+against the CPU oracle on the same seeded inputs.  Index maps, undistorted corners, residuals and
+Jacobians must be BIT-EXACT (the float32 projection rounding of multicam_mapper.cpp:644-648 leaves no
+room for a tolerance); sums of products (reduced system, costs, LM trajectory) are compared with the
+tolerances of BASELINE.json's north star written at each assert."""
+import copy
+
+import numpy as np
+import pytest
+
+from aar_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def binding():
+    from aar_b200 import binding as b
+    b.lib()
+    return b
+
+
+def small_rig(seed=3, **kw):
+    args = dict(C=3, M=6, F=40, obs_per_frame=6.0, seed=seed)
+    args.update(kw)
+    return synth.make_rig(**args)
+
+
+def test_index_maps_bit_exact(binding, oracle_mod):
+    rig = small_rig()
+    # detections of an unknown camera / marker / frame and a duplicated (frame, cam, marker) exercise the erasures
+    extra_f = np.array([rig.frame_ids[0], rig.frame_ids[1], 10 ** 6, rig.det_frame[5]], np.int32)
+    extra_c = np.array([99, rig.cam_ids[1], rig.cam_ids[0], rig.det_cam[5]], np.int32)
+    extra_m = np.array([rig.marker_ids[0], 12345, rig.marker_ids[0], rig.det_marker[5]], np.int32)
+    rig.det_frame = np.concatenate([rig.det_frame, extra_f]); rig.det_cam = np.concatenate([rig.det_cam, extra_c])
+    rig.det_marker = np.concatenate([rig.det_marker, extra_m])
+    rig.det_xy = np.concatenate([rig.det_xy, rig.det_xy[:4] + 1.0])
+    # the oracle cannot hold a frame without a pose (the reference would throw): drop that one for it
+    keep = rig.det_frame != 10 ** 6
+    rig_o = copy.copy(rig)
+    rig_o.det_frame, rig_o.det_cam, rig_o.det_marker, rig_o.det_xy = rig.det_frame[keep], rig.det_cam[keep], rig.det_marker[keep], rig.det_xy[keep]
+    o = oracle_mod.Oracle(rig_o)
+    p = binding.Problem(rig)
+    obs = o.observations(); maps = p.index_maps()
+    assert p.num_obs == len(obs["frame_id"])
+    assert np.array_equal(rig.frame_ids[maps["frame_idx"]], obs["frame_id"])
+    assert np.array_equal(rig.cam_ids[maps["cam_idx"]], obs["cam_id"])
+    assert np.array_equal(rig.marker_ids[maps["marker_idx"]], obs["marker_id"])
+    assert np.array_equal(maps["has_jac"], obs["has_jac"]) and (obs["has_jac"] == 0).sum() == 1
+    assert p.num_vars == o.num_vars
+    und, raw = p.observations()
+    assert np.array_equal(und, obs["und"]) and np.array_equal(raw[obs["has_jac"] == 1], obs["raw"][obs["has_jac"] == 1])
+    # Jacobian sparsity pattern bit-exact (explicit zeros kept), values bit-exact
+    z = o.mats2evec()
+    cp_o, ri_o, v_o = o.jacobian(z)
+    cp_g, ri_g, v_g = p.jacobian(z)
+    assert np.array_equal(cp_o, cp_g) and np.array_equal(ri_o, ri_g)
+    assert np.array_equal(v_o, v_g)
+    r_g, _ = p.residual(z)
+    assert np.array_equal(r_g, o.error(z))
+
+
+@pytest.mark.parametrize("distorted", [False, True])
+def test_residual_and_jacobian_bit_exact(binding, oracle_mod, distorted):
+    rig = small_rig(seed=5, distorted=distorted, F=60)
+    o = oracle_mod.Oracle(rig, sincos_mode=1)
+    p = binding.Problem(rig)
+    und, raw = p.observations()
+    obs = o.observations()
+    assert np.array_equal(und, obs["und"])                      # device undistortion == cv::undistortPoints restatement
+    if distorted:
+        assert not np.array_equal(und, raw)
+    rng = np.random.default_rng(0)
+    z0 = o.mats2evec()
+    assert np.abs(p.mats2evec() - z0).max() < 1e-12
+    for z in (z0, z0 + rng.normal(0, 1e-2, z0.shape)):
+        r_o = o.error(z)
+        r_g, ss = p.residual(z)
+        assert np.array_equal(r_g, r_o)                             # bit-exact residuals
+        assert abs(ss - r_o @ r_o) <= 1e-12 * (r_o @ r_o)           # summation order only
+        cp_o, ri_o, v_o = o.jacobian(z)
+        cp_g, ri_g, v_g = p.jacobian(z)
+        assert np.array_equal(cp_o, cp_g) and np.array_equal(ri_o, ri_g)
+        assert np.array_equal(v_o, v_g)                             # bit-exact quantised central differences
+    # against the libm-sincos oracle (what cv::Rodrigues computes) count float flips: expected 0 at this size
+    o.set_sincos_mode(0)
+    flips = (o.error(z0) != p.residual(z0)[0]).sum()
+    o.set_sincos_mode(1)
+    assert flips <= 2
+
+
+def test_config_flags_and_huber(binding, oracle_mod):
+    rig = small_rig(seed=7)
+    for cams, markers, objects in [(False, True, True), (True, False, True), (True, True, False), (False, False, True)]:
+        o = oracle_mod.Oracle(rig); o.set_config(cams=cams, markers=markers, objects=objects)
+        p = binding.Problem(rig, cams=cams, markers=markers, objects=objects)
+        z = o.mats2evec()
+        assert p.num_vars == o.num_vars == len(z)
+        assert np.array_equal(p.residual(z)[0], o.error(z))
+        cp_o, ri_o, v_o = o.jacobian(z); cp_g, ri_g, v_g = p.jacobian(z)
+        assert np.array_equal(cp_o, cp_g) and np.array_equal(ri_o, ri_g) and np.array_equal(v_o, v_g)
+    o = oracle_mod.Oracle(rig); o.set_config(with_huber=True, huber_delta=1.5)
+    p = binding.Problem(rig, with_huber=True)
+    z = o.mats2evec()
+    assert np.array_equal(p.residual(z, huber_delta=1.5)[0], o.error(z))
+
+
+def test_reduced_system_matches_oracle(binding, oracle_mod):
+    rig = small_rig(seed=9, F=50)
+    o = oracle_mod.Oracle(rig); p = binding.Problem(rig)
+    z = o.mats2evec(); mu = 1234.5
+    S_o, b_o, c_o = o.reduced_system(z, mu)
+    S_g, b_g, c_g = p.reduced_system(z, mu)
+    iu = np.triu_indices(p.n_r)
+    scale = np.abs(S_o).max()
+    assert np.abs(S_g[iu] - S_o[iu]).max() <= 1e-10 * scale        # sums of products in a different order
+    assert np.abs(b_g - b_o).max() <= 1e-10 * np.abs(b_o).max()
+    assert abs(c_g - c_o) <= 1e-12 * c_o
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_lm_solve_matches_reference_solver(binding, oracle_mod, name):
+    """MultiCamMapper::solve(): device-resident LM vs the oracle driving the reference sparselevmarq.h."""
+    rig = synth.make_config(name)
+    o = oracle_mod.Oracle(rig); p = binding.Problem(rig)
+    z0 = o.mats2evec()
+    z_o, fc_o, it_o, tr_o = o.solve(z0)
+    z_g, fc_g, it_g, tr_g = p.solve(z0)
+    n = min(it_o, it_g)
+    assert abs(it_o - it_g) <= 1                                      # stop rule may fire one iteration apart
+    assert np.abs(tr_g[:n, 0] - tr_o[:n, 0]).max() <= 1e-8 * tr_o[0, 0]   # per-iteration cost
+    assert np.allclose(tr_g[:n, 1], tr_o[:n, 1], rtol=1e-6)               # damping
+    assert abs(fc_g - fc_o) <= 1e-6 * fc_o                                # north star: final cost within 1e-6 relative
+    Tc_o, Tm_o, Tf_o = o.evec2mats(z_o); Tc_g, Tm_g, Tf_g = p.evec2mats(z_g)
+    for A, B in ((Tc_o, Tc_g), (Tm_o, Tm_g), (Tf_o, Tf_g)):
+        assert np.abs(A - B).max() <= 1e-6                               # poses within 1e-6
+    # and the solve actually recovers the synthetic ground truth (markers to a few mm)
+    assert np.abs(Tm_g[:, :3, 3] - rig.T_marker_true[:, :3, 3]).max() < 5e-3
+
+
+def test_lm_with_huber_matches_oracle(binding, oracle_mod):
+    rig = synth.make_config("cfg1", seed=21)
+    rig.det_xy[::37] += 25.0                                            # outliers
+    o = oracle_mod.Oracle(rig); o.set_config(with_huber=True)
+    p = binding.Problem(rig, with_huber=True)
+    z0 = o.mats2evec()
+    z_o, fc_o, it_o, tr_o = o.solve(z0)
+    z_g, fc_g, it_g, tr_g = p.solve(z0)
+    n = min(it_o, it_g)
+    assert abs(it_o - it_g) <= 1
+    assert np.abs(tr_g[:n, 0] - tr_o[:n, 0]).max() <= 1e-8 * tr_o[0, 0]
+    assert np.abs(z_g - z_o).max() <= 1e-6 * max(1.0, np.abs(z_o).max())
+
+
+def test_full_size_properties_cfg3(binding, oracle_mod):
+    """cfg 3 (8 cams, 24 markers, 10k frames, ~0.5M observations): residuals bit-exact against the oracle;
+    the cost decreases monotonically to the noise floor and the oracle confirms the final cost."""
+    rig = synth.make_config("cfg3")
+    o = oracle_mod.Oracle(rig); p = binding.Problem(rig)
+    z0 = o.mats2evec()
+    r_o = o.error(z0); r_g, ss = p.residual(z0)
+    assert np.array_equal(r_g, r_o)
+    z_g, fc, it, tr = p.solve(z0)
+    assert np.all(np.diff(tr[:, 0]) < 0)
+    rms = np.sqrt(fc / (8 * p.num_obs))
+    assert 0.25 < rms < 0.35                                             # 0.3 px corner noise
+    r_fin = o.error(z_g)
+    assert abs(r_fin @ r_fin - fc) <= 1e-9 * fc
