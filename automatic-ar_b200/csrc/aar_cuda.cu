@@ -99,7 +99,7 @@ struct aar_problem {
     DevProblem dp{};
     // ---- LM host mirror
     aar_lm_params params{};
-    bool lm_active = false;
+    bool lm_active = false, have_z0 = false;
     float huber_cur = 2.5f, huber_eval = 2.5f;
     double prev_cost = 0, cost = 0, initial_cost = 0;
     int iter = 0; int exit_code = 0; long long total_tries = 0;
@@ -107,7 +107,7 @@ struct aar_problem {
     ncclComm_t comm = nullptr;
     // ---- instrumentation
     long long launches = 0; bool profiling = false;
-    cudaEvent_t ev[8] = {}; double phase_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[10] = {}; double phase_ms[AAR_NUM_PHASES] = {};
 };
 
 namespace {
@@ -158,13 +158,17 @@ int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_ou
     return AAR_OK;
 }
 
+void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
+
 constexpr size_t JAC_SMEM = (size_t)144 * JAC_BLOCK * sizeof(double);
 
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     expand(p, p->d_z.p, 0);
     if (p->dp.N == 0) return AAR_OK;
+    prof_mark(p, 7);
     if (Jdump) LAUNCH(p, k_jacobian<false>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, nullptr, nullptr, nullptr, nullptr, Jdump);
     else LAUNCH(p, k_jacobian<true>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, nullptr);
+    prof_mark(p, 8);
     return AAR_OK;
 }
 
@@ -212,8 +216,6 @@ int push_state(aar_problem *p) {
     CU(cudaMemcpyAsync(p->d_st.p, p->h_st, sizeof(LmState), cudaMemcpyHostToDevice, p->stream));
     return AAR_OK;
 }
-
-void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
 
 } // namespace
 
@@ -590,11 +592,17 @@ int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, do
 
 // ------------------------------------------------------------------------------- LM loop ----
 int aar_lm_begin(aar_problem *p, const double *z0, const aar_lm_params *params) {
-    if (!p || !z0) return AAR_ERR_INVALID;
+    if (!p) return AAR_ERR_INVALID;
+    if (!z0 && !p->have_z0) { set_err("aar_lm_begin(z0 = NULL) restarts from the previous z0, but there is none"); return AAR_ERR_INVALID; }
     CU(cudaSetDevice(p->device));
     if (params) p->params = *params; else aar_lm_default_params(&p->params);
-    int rc = upload_z(p, z0, p->d_z.p); if (rc) return rc;
-    if (p->n_vars > 0) CU(cudaMemcpyAsync(p->d_z0.p, p->d_z.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    int rc = AAR_OK;
+    if (z0) {
+        if ((rc = upload_z(p, z0, p->d_z.p))) return rc;
+        if (p->n_vars > 0) CU(cudaMemcpyAsync(p->d_z0.p, p->d_z.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        p->have_z0 = true;
+    } else if (p->n_vars > 0) // restart from the starting point that is already resident on the device
+        CU(cudaMemcpyAsync(p->d_z.p, p->d_z0.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     // MultiCamMapper::solve: hubberDelta = 10 before the solver starts (multicam_mapper.cpp:425)
     p->huber_cur = 10.f; p->huber_eval = 10.f;
     // SparseLevMarq::init (sparselevmarq.h:237-249)
@@ -668,7 +676,10 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             if (p->profiling) {
                 cudaEventSynchronize(p->ev[6]);
                 float ms;
-                if (ntries == 0) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+                if (ntries == 0) {
+                    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms;
+                    cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+                }
                 cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
                 cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
                 cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->phase_ms[3] += ms;
@@ -757,9 +768,9 @@ int aar_comm_init(aar_problem *p, const void *id128) {
 
 int64_t aar_kernel_launches(const aar_problem *p) { return p ? p->launches : 0; }
 int aar_set_profiling(aar_problem *p, int32_t on) { if (!p) return AAR_ERR_INVALID; p->profiling = on != 0; for (double &m : p->phase_ms) m = 0; return AAR_OK; }
-int aar_get_phase_ms(const aar_problem *p, double *a, double *b, double *c, double *d, double *e) {
-    if (!p) return AAR_ERR_INVALID;
-    if (a) *a = p->phase_ms[0]; if (b) *b = p->phase_ms[1]; if (c) *c = p->phase_ms[2]; if (d) *d = p->phase_ms[3]; if (e) *e = p->phase_ms[4];
+int aar_get_phase_ms(const aar_problem *p, double *ms) {
+    if (!p || !ms) return AAR_ERR_INVALID;
+    for (int i = 0; i < AAR_NUM_PHASES; i++) ms[i] = p->phase_ms[i];
     return AAR_OK;
 }
 

@@ -216,10 +216,19 @@ class Problem:
         self.last_report = rep
         return z, rep.final_cost, rep.iterations, self._trace_array(rep, tr)
 
-    def lm_begin(self, z0, params=None):
-        z = np.ascontiguousarray(z0, np.float64)
+    def solve_inplace(self, z, params=None):
+        """aar_lm_solve on a caller-owned (e.g. pinned) float64 array, in place; returns the report."""
+        assert z.dtype == np.float64 and z.flags["C_CONTIGUOUS"]
+        rep, _ = self._report(1)
         p = params if params is not None else self.default_params()
-        _chk(lib().aar_lm_begin(self.h, _vp(z), C.byref(p)), "aar_lm_begin")
+        _chk(lib().aar_lm_solve(self.h, _vp(z), C.byref(p), C.byref(rep)), "aar_lm_solve")
+        return rep
+
+    def lm_begin(self, z0=None, params=None):
+        """z0 = None restarts from the z0 of the previous lm_begin (device resident, no copy)."""
+        z = None if z0 is None else np.ascontiguousarray(z0, np.float64)
+        p = params if params is not None else self.default_params()
+        _chk(lib().aar_lm_begin(self.h, None if z is None else _vp(z), C.byref(p)), "aar_lm_begin")
 
     def lm_iterate(self, n, trace_capacity=0):
         rep, tr = self._report(max(trace_capacity, 1))
@@ -237,9 +246,9 @@ class Problem:
         _chk(lib().aar_set_profiling(self.h, C.c_int32(int(on))), "aar_set_profiling")
 
     def phase_ms(self):
-        v = [C.c_double(0) for _ in range(5)]
-        _chk(lib().aar_get_phase_ms(self.h, *[C.byref(x) for x in v]), "aar_get_phase_ms")
-        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm"], [x.value for x in v]))
+        v = (C.c_double * 7)()
+        _chk(lib().aar_get_phase_ms(self.h, v), "aar_get_phase_ms")
+        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm", "jacobian_kernel", "jacobian_launches"], list(v)))
 
 
 def comm_unique_id() -> bytes:

@@ -125,7 +125,7 @@ def _distort(xn, yn, d):
 
 def make_rig(C, M, F, obs_per_frame, seed=0, marker_size=0.05, noise_px=0.3, distorted=False,
              rot_sigma=0.02, trans_sigma=0.005, shuffle_detections=True, sparse_marker_ids=True,
-             chunk_frames=2000) -> Rig:
+             chunk_frames=4000) -> Rig:
     rng = np.random.default_rng(seed)
     W, H = 1280, 720
     # cameras on a ring of radius 1.5 m looking at the origin (world frame), slightly varied height
@@ -173,12 +173,15 @@ def make_rig(C, M, F, obs_per_frame, seed=0, marker_size=0.05, noise_px=0.3, dis
     # estimate visibility rate on the first chunk to set the Bernoulli thinning probability
     p_keep = None
     Tci = se3_inv(T_cam_true)                                # root camera -> camera
+    Yall = np.concatenate([T_marker_true[m] @ Xm for m in range(M)], axis=1)                      # (4, 4M) corners in the root-marker frame
+    NCm = np.stack([np.stack([T_marker_true[m][:, 2], T_marker_true[m][:, 3]], axis=1) for m in range(M)], axis=1).reshape(4, 2 * M)
     for f0 in range(0, F, chunk_frames):
         f1 = min(F, f0 + chunk_frames)
         n = f1 - f0
-        # T[f,c,m] = inv(Tc) * To * Tm   -> (n,C,M,4,4)
-        A = Tci[None, :, None] @ T_frame_all[f0:f1, None, None] @ T_marker_true[None, None, :]
-        P = A[..., :3, :] @ Xm                               # (n,C,M,3,4) camera-frame corner coordinates
+        # T1[f,c] = inv(Tc) * To ; corners and normals of every marker in the object frame are fixed, so
+        # the camera-frame corners are one (n*C*3, 4) x (4, 4M) product
+        T1 = np.einsum("cij,fjk->fcik", Tci, T_frame_all[f0:f1])           # (n,C,4,4)
+        P = (T1[:, :, :3, :].reshape(n * C * 3, 4) @ Yall).reshape(n, C, 3, M, 4).transpose(0, 1, 3, 2, 4)  # (n,C,M,3,4)
         z = P[..., 2, :]
         xn = P[..., 0, :] / z; yn = P[..., 1, :] / z
         if distorted:
@@ -189,7 +192,8 @@ def make_rig(C, M, F, obs_per_frame, seed=0, marker_size=0.05, noise_px=0.3, dis
             xd, yd = xn, yn
         u = xd * K[None, :, None, None, 0, 0] + K[None, :, None, None, 0, 2]
         v = yd * K[None, :, None, None, 1, 1] + K[None, :, None, None, 1, 2]
-        normal = A[..., :3, 2]; centre = A[..., :3, 3]
+        NC = (T1[:, :, :3, :].reshape(n * C * 3, 4) @ NCm).reshape(n, C, 3, M, 2)      # normal (w=0) and centre (w=1)
+        normal = NC[..., 0].transpose(0, 1, 3, 2); centre = NC[..., 1].transpose(0, 1, 3, 2)
         view = centre / np.linalg.norm(centre, axis=-1, keepdims=True)
         facing = (normal * view).sum(-1) < -0.2
         inside = ((u > 1) & (u < W - 2) & (v > 1) & (v < H - 2) & (z > 0.1)).all(-1)

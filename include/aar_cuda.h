@@ -132,7 +132,8 @@ int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, do
  * sparselevmarq.h:439-472): z is in/out like io_vec; the loop is device resident. */
 int aar_lm_solve(aar_problem *p, double *z_inout, const aar_lm_params *params, aar_lm_report *report);
 /* the same in three steps, z staying on the device in between (bench / step-by-step mode,
- * SparseLevMarq::init + step, sparselevmarq.h:88-96) */
+ * SparseLevMarq::init + step, sparselevmarq.h:88-96).  aar_lm_begin(p, NULL, params) restarts from the z0 of
+ * the previous aar_lm_begin, which is still resident on the device (no host->device copy). */
 int aar_lm_begin(aar_problem *p, const double *z0, const aar_lm_params *params);
 int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *report);
 int aar_lm_end(aar_problem *p, double *z_out);
@@ -146,11 +147,14 @@ int aar_track_batch(aar_problem *p, double *z6_inout, const aar_lm_params *param
 int aar_comm_unique_id(void *id128);
 int aar_comm_init(aar_problem *p, const void *id128);
 
-/* instrumentation for bench.py: kernels launched by this handle so far, and per-phase device time
- * (ms) of the last aar_lm_iterate call when profiling was requested */
+/* instrumentation for bench.py: kernels launched by this handle so far, and device time (ms, CUDA events on
+ * the handle's stream) accumulated per phase since aar_set_profiling(p, 1):
+ *   [0] expansion + Jacobian/normal-equation assembly  [1] Schur + all-reduce + reduced solve  [2] back-substitution
+ *   [3] trial residual  [4] cost all-reduce + decision  [5] the Jacobian kernel alone  [6] number of Jacobian launches in [5] */
+#define AAR_NUM_PHASES 7
 int64_t aar_kernel_launches(const aar_problem *p);
 int aar_set_profiling(aar_problem *p, int32_t on);
-int aar_get_phase_ms(const aar_problem *p, double *jac_ms, double *schur_ms, double *solve_ms, double *resid_ms, double *comm_ms);
+int aar_get_phase_ms(const aar_problem *p, double *ms /* [AAR_NUM_PHASES] */);
 
 #ifdef __cplusplus
 }

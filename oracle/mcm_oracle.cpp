@@ -756,6 +756,8 @@ void aar_oracle_set_config(OracleHandle *h, int cams, int markers, int objects, 
     Config c; c.optimize_cam_poses = cams; c.optimize_marker_poses = markers; c.optimize_object_poses = objects; c.optimize_cam_intrinsics = intrinsics;
     h->mcm.set_config(c); h->mcm.with_huber = with_huber != 0; h->mcm.hubberDelta = huber_delta;
 }
+/* SparseLevMarq::Params::maxIters as MultiCamMapper sets it (mcm.cpp:326-330); tests lower it to compare single LM steps */
+void aar_oracle_set_max_iters(OracleHandle *h, int max_iters) { h->mcm.maxIters = max_iters; }
 int64_t aar_oracle_num_vars(OracleHandle *h) { return (int64_t)h->mcm.num_vars; }
 int64_t aar_oracle_num_rows(OracleHandle *h) { return (int64_t)h->mcm.num_point_xys; }
 

@@ -88,6 +88,9 @@ class Oracle:
         self.L.aar_oracle_set_config(self.h, C.c_int(cams), C.c_int(markers), C.c_int(objects), C.c_int(intrinsics),
                                      C.c_int(with_huber), C.c_float(huber_delta))
 
+    def set_max_iters(self, n):
+        self.L.aar_oracle_set_max_iters(self.h, C.c_int(int(n)))
+
     @property
     def num_vars(self): return int(self.L.aar_oracle_num_vars(self.h))
     @property
