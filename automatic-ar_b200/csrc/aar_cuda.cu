@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -91,11 +92,19 @@ struct aar_problem {
     cudaStream_t stream = nullptr; bool own_stream = false;
     DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
-    DevBuf<double> d_intr, d_K9, d_dist5, d_camv, d_mkv, d_frv, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
+    DevBuf<int> d_frame_cs_cum;
+    DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
     DevBuf<LmState> d_st;
     DevBuf<int> d_flag;
-    LmState *h_st = nullptr; double *h_red3 = nullptr; // pinned
+    LmState *h_st = nullptr; double *h_red3 = nullptr; int *h_flags = nullptr; // pinned
+    // ---- Jacobian kernel plans (chunks of observations per persistent CTA), built per staging type
+    struct JacPlanDev { DevBuf<int4> chunks; DevBuf<int> cta_ptr; JacPlan pl{}; int T = 0, grid = 0; size_t smem = 0; bool built = false; };
+    JacPlanDev plan_f32, plan_f64;
+    std::vector<int> h_obs_f, h_frame_obs_ptr, h_frame_ms_cum;   // local frame of each local observation; CSR; marker-slot prefix
+    int max_ms = 0, num_sms = 148; size_t smem_optin = 227 * 1024;
+    int force_exact_staging = 0; long long exact_reruns = 0; int *h_dbg = nullptr;
+    void (*jac_fn[2])(DevProblem, JacPlan, float, double *, double *, double *, double *, int *) = {nullptr, nullptr};
     DevProblem dp{};
     // ---- LM host mirror
     aar_lm_params params{};
@@ -141,18 +150,9 @@ int allreduce(aar_problem *p, double *buf, size_t n, ncclRedOp_t op) {
     return AAR_OK;
 }
 
-// expands z (device) into the pose tables; trial != 0 -> base-only trial tables
-int expand(aar_problem *p, const double *dz, int trial) {
-    const int jobs = p->C * (trial ? 1 : NVAR_CAM) + p->M * (trial ? 1 : NVAR_RT);
-    LAUNCH(p, k_expand_rig, cdiv(jobs, 128), 128, 0, p->dp, dz, trial);
-    const long long fj = (long long)p->dp.F * (trial ? 1 : NVAR_RT);
-    if (fj > 0) LAUNCH(p, k_expand_frames, cdiv(fj, 128), 128, 0, p->dp, dz, trial);
-    return AAR_OK;
-}
-
 // residual sum of squares at dz into d_red3[0] (must be zeroed by the caller); optional residual vector
 int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_out) {
-    expand(p, dz, 1);
+    LAUNCH(p, k_expand_trial, cdiv((long long)p->C + p->M + p->dp.F, 128), 128, 0, p->dp, dz);
     if (p->dp.N > 0)
         LAUNCH(p, k_residual, cdiv(p->dp.N, 256), 256, 0, p->dp, p->d_cam_tr.p, POSE_STRIDE, p->d_mk_tr.p, POSE_STRIDE, p->d_fr_tr.p, POSE_STRIDE, huber_delta, d_r_out, p->d_red3.p);
     return AAR_OK;
@@ -160,25 +160,115 @@ int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_ou
 
 void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
 
-constexpr size_t JAC_SMEM = (size_t)144 * JAC_BLOCK * sizeof(double);
+using JacFn = void (*)(DevProblem, JacPlan, float, double *, double *, double *, double *, int *);
+struct JacVariant { int T; size_t elem; JacFn fn; };
+const JacVariant JAC_F32[] = {{256, 4, k_jacobian<float, 256>}, {224, 4, k_jacobian<float, 224>}, {192, 4, k_jacobian<float, 192>}, {128, 4, k_jacobian<float, 128>}, {64, 4, k_jacobian<float, 64>}};
+const JacVariant JAC_F64[] = {{96, 8, k_jacobian<double, 96>}, {32, 8, k_jacobian<double, 32>}};
 
+// Plans the persistent Jacobian kernel: picks the largest CTA size whose shared-memory carve-up fits, splits the
+// local observations into frame-aligned contiguous ranges (one per CTA) and each range into chunks of <= T
+// observations whose live marker slots fit the W_m ring.
+int build_jac_plan(aar_problem *p, aar_problem::JacPlanDev &P, bool exact) {
+    const long long Nl = p->dp.N; const int Fl = p->dp.F;
+    const JacVariant *vars = exact ? JAC_F64 : JAC_F32; const int nvars = exact ? 2 : 5;
+    const size_t budget = p->smem_optin - 1024;   // static shared memory + reserve
+    const size_t hcm_d = (size_t)p->nrc * p->nrm * 36, tab_d = (size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB, fix_d = (size_t)(p->nrc + p->nrm) * 27;
+    const bool hcm_smem = hcm_d * 8 <= 48 * 1024, tabs_smem = tab_d * 8 <= 64 * 1024;
+    const size_t fixed = 8 * (fix_d + (hcm_smem ? hcm_d : 0) + (tabs_smem ? tab_d : 0));
+    const int need_cap = std::max(p->max_ms, 1);
+    int pick = -1; long long cap_max = 0;
+    for (int i = 0; i < nvars; i++) {
+        const size_t j = (size_t)144 * vars[i].T * vars[i].elem;
+        if (fixed + j + (size_t)need_cap * 288 > budget) continue;
+        cap_max = (long long)((budget - fixed - j) / 288);
+        pick = i; break;
+    }
+    if (pick < 0) { set_err("the Jacobian kernel's shared-memory carve-up does not fit (%d markers seen in one frame, %d cameras, %d markers)", p->max_ms, p->C, p->M); return AAR_ERR_UNSUPPORTED; }
+    const int T = vars[pick].T;
+    cap_max = std::min<long long>(cap_max, std::max<long long>(2LL * need_cap + 8, 64));
+    // CTA ranges: frame aligned, balanced by observation count
+    const int grid = (int)std::max<long long>(1, std::min<long long>(p->num_sms, (Nl + T - 1) / T));
+    std::vector<int> cta_ptr((size_t)grid + 1, 0);
+    std::vector<int4> chunks;
+    const std::vector<int> &fop = p->h_frame_obs_ptr, &ms = p->h_frame_ms_cum, &of = p->h_obs_f;
+    int used_cap = 1, fa = 0;
+    for (int b = 0; b < grid; b++) {
+        int fb = Fl;
+        if (b + 1 < grid) {
+            const long long target = Nl * (b + 1) / grid;
+            fb = (int)(std::lower_bound(fop.begin(), fop.end(), (int)target) - fop.begin());
+            fb = std::min(std::max(fb, fa), Fl);
+        }
+        const int A = fop[(size_t)fa], B = fop[(size_t)fb];
+        int next_flush = fa, lo = A;
+        while (lo < B) {
+            int hi = std::min(lo + T, B);
+            const int f_first = of[(size_t)lo]; int f_last = of[(size_t)hi - 1];
+            while (ms[(size_t)f_last + 1] - ms[(size_t)f_first] > cap_max && f_last > f_first) { hi = fop[(size_t)f_last]; f_last = of[(size_t)hi - 1]; }
+            used_cap = std::max(used_cap, ms[(size_t)f_last + 1] - ms[(size_t)f_first]);
+            const int done_hi = hi == B ? fb : of[(size_t)hi];
+            chunks.push_back(make_int4(lo, hi, next_flush, done_hi));
+            next_flush = done_hi; lo = hi;
+        }
+        if (A == B && fb > fa) chunks.push_back(make_int4(A, A, fa, fb));   // frames without observations: nothing to flush, kept for symmetry
+        cta_ptr[(size_t)b + 1] = (int)chunks.size();
+        fa = fb;
+    }
+    if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, 0));
+    CU(P.chunks.alloc(chunks.size())); CU(P.cta_ptr.alloc(cta_ptr.size()));
+    CU(cudaMemcpyAsync(P.chunks.p, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(P.cta_ptr.p, cta_ptr.data(), cta_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    P.T = T; P.grid = grid;
+    P.pl.chunks = P.chunks.p; P.pl.cta_chunk_ptr = P.cta_ptr.p; P.pl.slot_cap = used_cap; P.pl.hcm_smem = hcm_smem; P.pl.tabs_smem = tabs_smem;
+    P.pl.s1 = 1.0 / (2 * p->J_delta); P.pl.s2 = P.pl.s1 * P.pl.s1;
+    { const char *e = getenv("AAR_DEBUG_SKIP"); P.pl.skip = e ? atoi(e) : 0; }
+    P.smem = fixed + (size_t)used_cap * 288 + (size_t)144 * T * vars[pick].elem;
+    CU(cudaFuncSetAttribute(vars[pick].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    P.built = true;
+    P.pl.chunks = P.chunks.p;
+    p->jac_fn[exact ? 1 : 0] = vars[pick].fn;
+    return AAR_OK;
+}
+
+// J^T J blocks and J^T r at d_z (sparselevmarq.h:353-367) into Hf / W / Hrr / gr; or the dense per-observation
+// Jacobian blocks into Jdump (parity hook)
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
-    expand(p, p->d_z.p, 0);
+    const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
+    LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
     if (p->dp.N == 0) return AAR_OK;
-    prof_mark(p, 7);
-    if (Jdump) LAUNCH(p, k_jacobian<false>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, nullptr, nullptr, nullptr, nullptr, Jdump);
-    else LAUNCH(p, k_jacobian<true>, cdiv(p->dp.N, JAC_BLOCK), JAC_BLOCK, JAC_SMEM, p->dp, huber_eval, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, nullptr);
-    prof_mark(p, 8);
+    if (Jdump) { LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool exact = p->force_exact_staging || attempt == 1;
+        aar_problem::JacPlanDev &P = exact ? p->plan_f64 : p->plan_f32;
+        if (!P.built) { int rc = build_jac_plan(p, P, exact); if (rc) return rc; }
+        if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
+        if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
+        if (p->dp.F > 0) LAUNCH(p, k_zero_frame_sums, cdiv(p->dp.F, 8), 256, 0, p->dp, p->d_Hf.p, p->d_W.p);
+        prof_mark(p, 7);
+        p->jac_fn[exact ? 1 : 0]<<<P.grid, P.T, P.smem, p->stream>>>(p->dp, P.pl, huber_eval, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, p->d_flag.p);
+        p->launches++;
+        prof_mark(p, 8);
+        if (p->h_dbg) {   // development aid (AAR_DEBUG_MARKERS=1): watchdog on the kernel, dump the per-warp markers if it does not finish
+            for (int w = 0; w < 200 && cudaStreamQuery(p->stream) == cudaErrorNotReady; w++) usleep(50000);
+            if (cudaStreamQuery(p->stream) == cudaErrorNotReady) {
+                fprintf(stderr, "k_jacobian watchdog: grid %d T %d smem %zu slot_cap %d; markers per CTA/warp:\n", P.grid, P.T, P.smem, P.pl.slot_cap);
+                for (int w = 0; w < 8; w++) { fprintf(stderr, " warp %d:", w); for (int k = 0; k < 32; k++) fprintf(stderr, " %d", p->h_dbg[w * 32 + k]); fprintf(stderr, "\n"); }
+                fflush(stderr); _exit(3);
+            }
+        }
+        if (exact) break;
+        // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
+        CU(cudaMemcpyAsync(p->h_flags, p->d_flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        if (!p->h_flags[1]) break;
+        p->exact_reruns++;
+        CU(cudaMemsetAsync(p->d_flag.p + 1, 0, sizeof(int), p->stream));
+    }
     return AAR_OK;
 }
 
-int zero_normal_equations(aar_problem *p) {
-    if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
-    if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
-    if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
-    if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
-    return AAR_OK;
-}
+int zero_normal_equations(aar_problem *) { return AAR_OK; }   // zeroing is part of jacobian_accumulate
 
 __global__ void k_prepare_reduced(int n_r, const double *__restrict__ Hrr, const double *__restrict__ gr, double *__restrict__ red) {
     // red = [S (n_r*n_r) | b (n_r) | Br (n_r)]
@@ -306,25 +396,44 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     p->o_begin = frame_ptr[(size_t)p->f_begin]; p->o_end = frame_ptr[(size_t)p->f_end];
     const int Fl = p->f_end - p->f_begin; const long long Nl = p->o_end - p->o_begin;
 
-    // ---- W slots: per local frame, the distinct active camera / marker blocks seen
-    std::vector<int> slot_ptr((size_t)Fl + 1, 0), slot_block, slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
-    p->max_slots = 0;
+    // ---- W slots: per local frame, the distinct active camera blocks seen (order of first appearance), then the
+    // distinct active marker blocks; cs_cum / ms_cum are the running numbers of camera / marker slots
+    std::vector<int> slot_ptr((size_t)Fl + 1, 0), cs_cum((size_t)Fl + 1, 0), ms_cum((size_t)Fl + 1, 0), slot_block, slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
+    p->max_slots = 0; p->max_ms = 0;
+    if (Nl >= (1LL << 31) - 1) { set_err("more than 2^31 observations on one rank"); return AAR_ERR_UNSUPPORTED; }
     {
         std::vector<int> seen((size_t)(p->nrc + p->nrm), -1);
         for (int f = 0; f < Fl; f++) {
             const int base = (int)slot_block.size();
+            const long long o0 = frame_ptr[(size_t)(p->f_begin + f)], o1 = frame_ptr[(size_t)(p->f_begin + f) + 1];
             std::vector<int> touched;
-            for (long long o = frame_ptr[(size_t)(p->f_begin + f)]; o < frame_ptr[(size_t)(p->f_begin + f) + 1]; o++) {
-                if (!p->opt_f) break;
-                const int c = p->g_cam[(size_t)o], m = p->g_marker[(size_t)o];
-                if (p->opt_c && c != p->root_cam) { int b = c - (c > p->root_cam ? 1 : 0); if (seen[(size_t)b] < 0) { seen[(size_t)b] = (int)slot_block.size(); slot_block.push_back(b); touched.push_back(b); } slot_c[(size_t)(o - p->o_begin)] = seen[(size_t)b]; }
-                if (p->opt_m && m != p->root_marker) { int b = p->nrc + m - (m > p->root_marker ? 1 : 0); if (seen[(size_t)b] < 0) { seen[(size_t)b] = (int)slot_block.size(); slot_block.push_back(b); touched.push_back(b); } slot_m[(size_t)(o - p->o_begin)] = seen[(size_t)b]; }
-            }
-            for (int b : touched) seen[(size_t)b] = -1;
+            if (p->opt_f && p->opt_c)
+                for (long long o = o0; o < o1; o++) {
+                    const int c = p->g_cam[(size_t)o];
+                    if (c == p->root_cam) continue;
+                    const int bk = c - (c > p->root_cam ? 1 : 0);
+                    if (seen[(size_t)bk] < 0) { seen[(size_t)bk] = (int)slot_block.size(); slot_block.push_back(bk); touched.push_back(bk); }
+                    slot_c[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
+                }
+            const int ncs = (int)slot_block.size() - base;
+            if (p->opt_f && p->opt_m)
+                for (long long o = o0; o < o1; o++) {
+                    const int m = p->g_marker[(size_t)o];
+                    if (m == p->root_marker) continue;
+                    const int bk = p->nrc + m - (m > p->root_marker ? 1 : 0);
+                    if (seen[(size_t)bk] < 0) { seen[(size_t)bk] = (int)slot_block.size(); slot_block.push_back(bk); touched.push_back(bk); }
+                    slot_m[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
+                }
+            for (int bk : touched) seen[(size_t)bk] = -1;
+            const int nms = (int)slot_block.size() - base - ncs;
             slot_ptr[(size_t)f + 1] = (int)slot_block.size();
-            p->max_slots = std::max(p->max_slots, (int)slot_block.size() - base);
+            cs_cum[(size_t)f + 1] = cs_cum[(size_t)f] + ncs; ms_cum[(size_t)f + 1] = ms_cum[(size_t)f] + nms;
+            p->max_slots = std::max(p->max_slots, ncs + nms); p->max_ms = std::max(p->max_ms, nms);
         }
     }
+    p->h_frame_ms_cum = ms_cum;
+    p->h_frame_obs_ptr.resize((size_t)Fl + 1);
+    for (int f = 0; f <= Fl; f++) p->h_frame_obs_ptr[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin);
     p->nslots = (long long)slot_block.size();
 
     // ---- device
@@ -335,6 +444,12 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     for (auto &e : p->ev) CU(cudaEventCreate(&e));
     CU(cudaMallocHost((void **)&p->h_st, sizeof(LmState)));
     CU(cudaMallocHost((void **)&p->h_red3, 8 * sizeof(double)));
+    CU(cudaMallocHost((void **)&p->h_flags, 4 * sizeof(int)));
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && v > 0) p->num_sms = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) == cudaSuccess && v > 0) p->smem_optin = (size_t)v;
+    }
 
     std::vector<int> obs_f((size_t)Nl), obs_cm((size_t)Nl);
     std::vector<float4> raw_a((size_t)Nl), raw_b((size_t)Nl);
@@ -353,13 +468,14 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
 #define UP(buf, vec)                                                                                             \
     do { CU((buf).alloc((vec).size())); if ((vec).size()) CU(cudaMemcpyAsync((buf).p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream)); } while (0)
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
-    UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block);
+    UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block); UP(p->d_frame_cs_cum, cs_cum);
+    p->h_obs_f = obs_f;
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
     UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
     UP(p->d_cam_fixed, fixed_c); UP(p->d_mk_fixed, fixed_m); UP(p->d_fr_fixed, fixed_f);
 #undef UP
     CU(p->d_und_a.alloc((size_t)Nl)); CU(p->d_und_b.alloc((size_t)Nl));
-    CU(p->d_camv.alloc((size_t)p->C * NVAR_CAM * POSE_STRIDE)); CU(p->d_mkv.alloc((size_t)p->M * NVAR_RT * POSE_STRIDE)); CU(p->d_frv.alloc((size_t)std::max(Fl, 1) * NVAR_RT * POSE_STRIDE));
+    CU(p->d_cam_tab.alloc((size_t)p->C * CAM_TAB)); CU(p->d_mk_tab.alloc((size_t)p->M * MK_TAB)); CU(p->d_fr_tab.alloc((size_t)std::max(Fl, 1) * FR_TAB));
     CU(p->d_cam_tr.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_mk_tr.alloc((size_t)p->M * POSE_STRIDE)); CU(p->d_fr_tr.alloc((size_t)std::max(Fl, 1) * POSE_STRIDE));
     const size_t nz = (size_t)std::max<long long>(p->n_vars, 1);
     CU(p->d_z.alloc(nz)); CU(p->d_zt.alloc(nz)); CU(p->d_z0.alloc(nz));
@@ -379,7 +495,8 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
     dp.und_a = p->d_und_a.p; dp.und_b = p->d_und_b.p; dp.raw_a = p->d_raw_a.p; dp.raw_b = p->d_raw_b.p;
     dp.intr = p->d_intr.p; dp.frame_slot_ptr = p->d_frame_slot_ptr.p; dp.slot_block = p->d_slot_block.p;
-    dp.camv = p->d_camv.p; dp.mkv = p->d_mkv.p; dp.frv = p->d_frv.p; dp.cam_tr = p->d_cam_tr.p; dp.mk_tr = p->d_mk_tr.p; dp.fr_tr = p->d_fr_tr.p;
+    dp.frame_cs_cum = p->d_frame_cs_cum.p;
+    dp.cam_tab = p->d_cam_tab.p; dp.mk_tab = p->d_mk_tab.p; dp.fr_tab = p->d_fr_tab.p; dp.cam_tr = p->d_cam_tr.p; dp.mk_tr = p->d_mk_tr.p; dp.fr_tr = p->d_fr_tr.p;
     dp.cam_fixed = p->d_cam_fixed.p; dp.mk_fixed = p->d_mk_fixed.p; dp.fr_fixed = p->d_fr_fixed.p;
 
     // ---- remove_distortions (multicam_mapper.cpp:554-578) on the device: raw -> und.
@@ -401,8 +518,9 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
         CU(cudaMemcpyAsync(p->d_und_b.p, ub.data(), ub.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
         CU(cudaStreamSynchronize(p->stream));
     }
-    CU(cudaFuncSetAttribute(k_jacobian<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM));
-    CU(cudaFuncSetAttribute(k_jacobian<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM));
+    { const char *e = getenv("AAR_DEBUG_MARKERS"); if (e && *e == '1') { CU(cudaHostAlloc((void **)&p->h_dbg, 8 * 256 * sizeof(int), cudaHostAllocMapped)); std::memset(p->h_dbg, 0, 8 * 256 * sizeof(int)); int *dptr = nullptr; CU(cudaHostGetDevicePointer((void **)&dptr, p->h_dbg, 0)); p->dp.dbg = dptr; } }
+    { const char *e = getenv("AAR_FORCE_EXACT_STAGING"); p->force_exact_staging = e && *e == '1'; }   // test hook: FP64 staging of the Jacobian block
+    { int rc = build_jac_plan(p, p->force_exact_staging ? p->plan_f64 : p->plan_f32, p->force_exact_staging); if (rc) return rc; }
     if (schur_smem(p) > 48 * 1024) {
         if (schur_smem(p) > 227 * 1024) { set_err("frame sees too many blocks for the Schur kernel"); return AAR_ERR_UNSUPPORTED; }
         CU(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(p)));
@@ -422,6 +540,7 @@ void aar_problem_destroy(aar_problem *p) {
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_red3) cudaFreeHost(p->h_red3);
+    if (p->h_flags) cudaFreeHost(p->h_flags);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -498,7 +617,7 @@ int aar_evec2mats(aar_problem *p, const double *z, double *cam_T, double *marker
     int rc = upload_z(p, z, p->d_zt.p); if (rc) return rc;
     // trial tables hold the INVERSE camera transform; expand the cameras into a scratch via the marker path instead:
     // cameras are read back from the Jacobian tables' construction is inverse-only, so re-expand on the fly here.
-    expand(p, p->d_zt.p, 1);
+    LAUNCH(p, k_expand_trial, cdiv((long long)p->C + p->M + p->dp.F, 128), 128, 0, p->dp, p->d_zt.p);
     std::vector<double> mk(12 * (size_t)p->M), fr(12 * (size_t)std::max(p->dp.F, 1)), ci(12 * (size_t)p->C);
     CU(cudaMemcpyAsync(mk.data(), p->d_mk_tr.p, mk.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(fr.data(), p->d_fr_tr.p, fr.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));

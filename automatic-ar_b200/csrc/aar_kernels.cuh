@@ -27,15 +27,15 @@ struct DevProblem {
     const int *obs_slot_c, *obs_slot_m; // W slot of the camera / marker block in this frame, -1 if none
     const float4 *und_a, *und_b, *raw_a, *raw_b; // x0 y0 x1 y1 | x2 y2 x3 y3
     const double *intr;          // [C][4] fx cx fy cy
-    // frame CSR
+    // frame CSR of W slots: per frame the camera blocks seen (in order of first appearance), then the marker blocks
     const int *frame_slot_ptr;   // [F+1]
+    const int *frame_cs_cum;     // [F+1] camera slots before frame f (so the marker slots of f start at slot_ptr[f] + cs_cum[f+1] - cs_cum[f])
     const int *slot_block;       // [nslots] reduced block index
-    // pose tables
-    double *camv;                // [C][13][12] inverse of camera->root, variants
-    double *mkv;                 // [M][7][12]
-    double *frv;                 // [F][7][12]
+    // pose tables of the Jacobian kernel (aar_jacobian.cuh: CAM_TAB / MK_TAB / FR_TAB doubles per entity)
+    double *cam_tab, *mk_tab, *fr_tab;
     double *cam_tr, *mk_tr, *fr_tr; // trial (z + delta) tables, base only: [.][12]
     const double *cam_fixed, *mk_fixed, *fr_fixed; // host matrices [.][12] for non-optimised groups
+    volatile int *dbg;           // development aid: per-warp progress markers in mapped host memory (NULL normally)
 };
 
 __device__ __forceinline__ int obs_cam(int cm) { return cm & 0xfff; }
@@ -67,47 +67,33 @@ __device__ __forceinline__ void expand_variant(const double *z6, int variant, do
     rodrigues(rv[0], rv[1], rv[2], T.r);
 }
 
-// cams_vec2mats / markers_vec2mats (mcm.cpp:532-552) + the perturbed copies of
-// obtain_transformation_derivs.  One thread per (entity, variant).  nvar_c/nvar_rt = 1 expands
-// the base only (trial residual), into the *_tr tables when trial != 0.
-__global__ void k_expand_rig(DevProblem p, const double *__restrict__ z, int trial) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nvc = trial ? 1 : NVAR_CAM, nvm = trial ? 1 : NVAR_RT;
-    const int ncam_jobs = p.C * nvc;
-    if (t < ncam_jobs) {
-        int c = t / nvc, v = t % nvc;
-        double *dst = trial ? p.cam_tr + (size_t)c * POSE_STRIDE : p.camv + ((size_t)c * NVAR_CAM + v) * POSE_STRIDE;
-        Pose T, Ti;
-        if (c == p.root_cam) { if (v == 0) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; } return; }
-        if (p.opt_c) expand_variant(z + col_of_cam(p, c), v, p.J_delta, T);
-        else { if (v > 0) return; load_pose(T, p.cam_fixed + (size_t)c * POSE_STRIDE); }
+// cams_vec2mats / markers_vec2mats / object_poses_vec2mats (mcm.cpp:524-552) of a trial point z + delta:
+// base poses only, into the *_tr tables read by k_residual.  One thread per entity.
+__global__ void k_expand_trial(DevProblem p, const double *__restrict__ z) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Pose T, Ti;
+    if (t < p.C) {
+        const int c = (int)t;
+        double *dst = p.cam_tr + (size_t)c * POSE_STRIDE;
+        if (c == p.root_cam) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; return; }
+        if (p.opt_c) expand_variant(z + col_of_cam(p, c), 0, p.J_delta, T); else load_pose(T, p.cam_fixed + (size_t)c * POSE_STRIDE);
         inv_rigid_lu(T, Ti);
         store_pose(dst, Ti);
         return;
     }
-    t -= ncam_jobs;
-    if (t < p.M * nvm) {
-        int m = t / nvm, v = t % nvm;
-        double *dst = trial ? p.mk_tr + (size_t)m * POSE_STRIDE : p.mkv + ((size_t)m * NVAR_RT + v) * POSE_STRIDE;
-        Pose T;
-        if (m == p.root_marker) { if (v == 0) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; } return; }
-        if (p.opt_m) expand_variant(z + col_of_marker(p, m), v, p.J_delta, T);
-        else { if (v > 0) return; load_pose(T, p.mk_fixed + (size_t)m * POSE_STRIDE); }
+    t -= p.C;
+    if (t < p.M) {
+        const int m = (int)t;
+        double *dst = p.mk_tr + (size_t)m * POSE_STRIDE;
+        if (m == p.root_marker) { for (int i = 0; i < 12; i++) dst[i] = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0; return; }
+        if (p.opt_m) expand_variant(z + col_of_marker(p, m), 0, p.J_delta, T); else load_pose(T, p.mk_fixed + (size_t)m * POSE_STRIDE);
         store_pose(dst, T);
+        return;
     }
-}
-
-// object_poses_vec2mats (mcm.cpp:524-530) + perturbed rotations.
-__global__ void k_expand_frames(DevProblem p, const double *__restrict__ z, int trial) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nv = trial ? 1 : NVAR_RT;
-    if (t >= (long long)p.F * nv) return;
-    int f = (int)(t / nv), v = (int)(t % nv);
-    double *dst = trial ? p.fr_tr + (size_t)f * POSE_STRIDE : p.frv + ((size_t)f * NVAR_RT + v) * POSE_STRIDE;
-    Pose T;
-    if (p.opt_f) expand_variant(z + p.col_frame0 + 6 * (size_t)f, v, p.J_delta, T);
-    else { if (v > 0) return; load_pose(T, p.fr_fixed + (size_t)f * POSE_STRIDE); }
-    store_pose(dst, T);
+    t -= p.M;
+    if (t >= p.F) return;
+    if (p.opt_f) expand_variant(z + p.col_frame0 + 6 * (size_t)t, 0, p.J_delta, T); else load_pose(T, p.fr_fixed + (size_t)t * POSE_STRIDE);
+    store_pose(p.fr_tr + (size_t)t * POSE_STRIDE, T);
 }
 
 struct ObsCtx {
