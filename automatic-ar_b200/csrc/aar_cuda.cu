@@ -98,13 +98,10 @@ struct aar_problem {
     DevBuf<LmState> d_st;
     DevBuf<int> d_flag;
     LmState *h_st = nullptr; double *h_red3 = nullptr; int *h_flags = nullptr; // pinned
-    // ---- Jacobian kernel plans (chunks of observations per persistent CTA), built per staging type
-    struct JacPlanDev { DevBuf<int4> chunks; DevBuf<int> cta_ptr; JacPlan pl{}; int T = 0, grid = 0; size_t smem = 0; bool built = false; };
-    JacPlanDev plan_f32, plan_f64;
-    std::vector<int> h_obs_f, h_frame_obs_ptr, h_frame_ms_cum;   // local frame of each local observation; CSR; marker-slot prefix
+    // ---- staged central-difference numerators ([144][N] float32, or float64 in the exact fallback) and residuals ([8][N])
+    DevBuf<float> d_Jn32; DevBuf<double> d_Jn64, d_Rv;
     int max_ms = 0, num_sms = 148; size_t smem_optin = 227 * 1024;
-    int force_exact_staging = 0; long long exact_reruns = 0; int *h_dbg = nullptr;
-    void (*jac_fn[2])(DevProblem, JacPlan, float, double *, double *, double *, double *, int *) = {nullptr, nullptr};
+    int force_exact_staging = 0; long long exact_reruns = 0;
     DevProblem dp{};
     // ---- LM host mirror
     aar_lm_params params{};
@@ -116,7 +113,7 @@ struct aar_problem {
     ncclComm_t comm = nullptr;
     // ---- instrumentation
     long long launches = 0; bool profiling = false;
-    cudaEvent_t ev[10] = {}; double phase_ms[AAR_NUM_PHASES] = {};
+    cudaEvent_t ev[12] = {}; double phase_ms[AAR_NUM_PHASES] = {};
 };
 
 namespace {
@@ -160,74 +157,33 @@ int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_ou
 
 void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
 
-using JacFn = void (*)(DevProblem, JacPlan, float, double *, double *, double *, double *, int *);
-struct JacVariant { int T; size_t elem; JacFn fn; };
-const JacVariant JAC_F32[] = {{256, 4, k_jacobian<float, 256>}, {224, 4, k_jacobian<float, 224>}, {192, 4, k_jacobian<float, 192>}, {128, 4, k_jacobian<float, 128>}, {64, 4, k_jacobian<float, 64>}};
-const JacVariant JAC_F64[] = {{96, 8, k_jacobian<double, 96>}, {32, 8, k_jacobian<double, 32>}};
-
-// Plans the persistent Jacobian kernel: picks the largest CTA size whose shared-memory carve-up fits, splits the
-// local observations into frame-aligned contiguous ranges (one per CTA) and each range into chunks of <= T
-// observations whose live marker slots fit the W_m ring.
-int build_jac_plan(aar_problem *p, aar_problem::JacPlanDev &P, bool exact) {
-    const long long Nl = p->dp.N; const int Fl = p->dp.F;
-    const JacVariant *vars = exact ? JAC_F64 : JAC_F32; const int nvars = exact ? 2 : 5;
-    const size_t budget = p->smem_optin - 1024;   // static shared memory + reserve
-    const size_t hcm_d = (size_t)p->nrc * p->nrm * 36, tab_d = (size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB, fix_d = (size_t)(p->nrc + p->nrm) * 27;
-    const bool hcm_smem = hcm_d * 8 <= 48 * 1024, tabs_smem = tab_d * 8 <= 64 * 1024;
-    const size_t fixed = 8 * (fix_d + (hcm_smem ? hcm_d : 0) + (tabs_smem ? tab_d : 0));
-    const int need_cap = std::max(p->max_ms, 1);
-    int pick = -1; long long cap_max = 0;
-    for (int i = 0; i < nvars; i++) {
-        const size_t j = (size_t)144 * vars[i].T * vars[i].elem;
-        if (fixed + j + (size_t)need_cap * 288 > budget) continue;
-        cap_max = (long long)((budget - fixed - j) / 288);
-        pick = i; break;
-    }
-    if (pick < 0) { set_err("the Jacobian kernel's shared-memory carve-up does not fit (%d markers seen in one frame, %d cameras, %d markers)", p->max_ms, p->C, p->M); return AAR_ERR_UNSUPPORTED; }
-    const int T = vars[pick].T;
-    cap_max = std::min<long long>(cap_max, std::max<long long>(2LL * need_cap + 8, 64));
-    // CTA ranges: frame aligned, balanced by observation count
-    const int grid = (int)std::max<long long>(1, std::min<long long>(p->num_sms, (Nl + T - 1) / T));
-    std::vector<int> cta_ptr((size_t)grid + 1, 0);
-    std::vector<int4> chunks;
-    const std::vector<int> &fop = p->h_frame_obs_ptr, &ms = p->h_frame_ms_cum, &of = p->h_obs_f;
-    int used_cap = 1, fa = 0;
-    for (int b = 0; b < grid; b++) {
-        int fb = Fl;
-        if (b + 1 < grid) {
-            const long long target = Nl * (b + 1) / grid;
-            fb = (int)(std::lower_bound(fop.begin(), fop.end(), (int)target) - fop.begin());
-            fb = std::min(std::max(fb, fa), Fl);
-        }
-        const int A = fop[(size_t)fa], B = fop[(size_t)fb];
-        int next_flush = fa, lo = A;
-        while (lo < B) {
-            int hi = std::min(lo + T, B);
-            const int f_first = of[(size_t)lo]; int f_last = of[(size_t)hi - 1];
-            while (ms[(size_t)f_last + 1] - ms[(size_t)f_first] > cap_max && f_last > f_first) { hi = fop[(size_t)f_last]; f_last = of[(size_t)hi - 1]; }
-            used_cap = std::max(used_cap, ms[(size_t)f_last + 1] - ms[(size_t)f_first]);
-            const int done_hi = hi == B ? fb : of[(size_t)hi];
-            chunks.push_back(make_int4(lo, hi, next_flush, done_hi));
-            next_flush = done_hi; lo = hi;
-        }
-        if (A == B && fb > fa) chunks.push_back(make_int4(A, A, fa, fb));   // frames without observations: nothing to flush, kept for symmetry
-        cta_ptr[(size_t)b + 1] = (int)chunks.size();
-        fa = fb;
-    }
-    if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, 0));
-    CU(P.chunks.alloc(chunks.size())); CU(P.cta_ptr.alloc(cta_ptr.size()));
-    CU(cudaMemcpyAsync(P.chunks.p, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, p->stream));
-    CU(cudaMemcpyAsync(P.cta_ptr.p, cta_ptr.data(), cta_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
-    P.T = T; P.grid = grid;
-    P.pl.chunks = P.chunks.p; P.pl.cta_chunk_ptr = P.cta_ptr.p; P.pl.slot_cap = used_cap; P.pl.hcm_smem = hcm_smem; P.pl.tabs_smem = tabs_smem;
-    P.pl.s1 = 1.0 / (2 * p->J_delta); P.pl.s2 = P.pl.s1 * P.pl.s1;
-    { const char *e = getenv("AAR_DEBUG_SKIP"); P.pl.skip = e ? atoi(e) : 0; }
-    P.smem = fixed + (size_t)used_cap * 288 + (size_t)144 * T * vars[pick].elem;
-    CU(cudaFuncSetAttribute(vars[pick].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    P.built = true;
-    P.pl.chunks = P.chunks.p;
-    p->jac_fn[exact ? 1 : 0] = vars[pick].fn;
+// launches one of the two Jacobian kernels with the shared-memory carve-up it needs
+template <typename JT>
+int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
+    const size_t tab_bytes = ((size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB) * sizeof(double);
+    const int tabs_smem = tab_bytes <= 96 * 1024;
+    const size_t smem1 = tabs_smem ? tab_bytes : 0;
+    static thread_local const void *attr_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT>;
+    const size_t hcm_d = (size_t)p->nrc * p->nrm * 36;
+    const size_t scr = (size_t)ACC_WARPS * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
+    AccPlan pl; pl.hcm_smem = fix + hcm_d * 8 + scr <= 100 * 1024; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
+    const size_t smem2 = fix + (pl.hcm_smem ? hcm_d * 8 : 0) + scr;
+    if (smem2 > p->smem_optin - 1024) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
+    CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
+    CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    (void)attr_done;
+    const long long N = p->dp.N;
+    const int grid1 = (int)std::max<long long>(1, std::min<long long>(2LL * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
+    const int per_sm2 = smem2 <= 110 * 1024 ? 2 : 1;
+    const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm2 * p->num_sms, (N + ACC_WARPS * 32 - 1) / (ACC_WARPS * 32)));
+    prof_mark(p, 7);
+    k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p);
+    p->launches++;
+    prof_mark(p, 9);
+    k2<<<grid2, ACC_WARPS * 32, smem2, p->stream>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+    p->launches++;
+    prof_mark(p, 8);
     return AAR_OK;
 }
 
@@ -236,27 +192,20 @@ int build_jac_plan(aar_problem *p, aar_problem::JacPlanDev &P, bool exact) {
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
-    if (p->dp.N == 0) return AAR_OK;
-    if (Jdump) { LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
+    if (Jdump) { if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
+    const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool exact = p->force_exact_staging || attempt == 1;
-        aar_problem::JacPlanDev &P = exact ? p->plan_f64 : p->plan_f32;
-        if (!P.built) { int rc = build_jac_plan(p, P, exact); if (rc) return rc; }
         if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
         if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
-        if (p->dp.F > 0) LAUNCH(p, k_zero_frame_sums, cdiv(p->dp.F, 8), 256, 0, p->dp, p->d_Hf.p, p->d_W.p);
-        prof_mark(p, 7);
-        p->jac_fn[exact ? 1 : 0]<<<P.grid, P.T, P.smem, p->stream>>>(p->dp, P.pl, huber_eval, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, p->d_flag.p);
-        p->launches++;
-        prof_mark(p, 8);
-        if (p->h_dbg) {   // development aid (AAR_DEBUG_MARKERS=1): watchdog on the kernel, dump the per-warp markers if it does not finish
-            for (int w = 0; w < 200 && cudaStreamQuery(p->stream) == cudaErrorNotReady; w++) usleep(50000);
-            if (cudaStreamQuery(p->stream) == cudaErrorNotReady) {
-                fprintf(stderr, "k_jacobian watchdog: grid %d T %d smem %zu slot_cap %d; markers per CTA/warp:\n", P.grid, P.T, P.smem, P.pl.slot_cap);
-                for (int w = 0; w < 8; w++) { fprintf(stderr, " warp %d:", w); for (int k = 0; k < 32; k++) fprintf(stderr, " %d", p->h_dbg[w * 32 + k]); fprintf(stderr, "\n"); }
-                fflush(stderr); _exit(3);
-            }
-        }
+        if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
+        if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
+        if (N == 0) return AAR_OK;
+        if (p->d_Rv.n < 8 * N) CU(p->d_Rv.alloc(8 * N));
+        int rc;
+        if (exact) { if (p->d_Jn64.n < 144 * N) CU(p->d_Jn64.alloc(144 * N)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
+        else { if (p->d_Jn32.n < 144 * N) CU(p->d_Jn32.alloc(144 * N)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
+        if (rc) return rc;
         if (exact) break;
         // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
         CU(cudaMemcpyAsync(p->h_flags, p->d_flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
@@ -431,9 +380,6 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
             p->max_slots = std::max(p->max_slots, ncs + nms); p->max_ms = std::max(p->max_ms, nms);
         }
     }
-    p->h_frame_ms_cum = ms_cum;
-    p->h_frame_obs_ptr.resize((size_t)Fl + 1);
-    for (int f = 0; f <= Fl; f++) p->h_frame_obs_ptr[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin);
     p->nslots = (long long)slot_block.size();
 
     // ---- device
@@ -469,7 +415,7 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     do { CU((buf).alloc((vec).size())); if ((vec).size()) CU(cudaMemcpyAsync((buf).p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream)); } while (0)
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
     UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block); UP(p->d_frame_cs_cum, cs_cum);
-    p->h_obs_f = obs_f;
+
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
     UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
     UP(p->d_cam_fixed, fixed_c); UP(p->d_mk_fixed, fixed_m); UP(p->d_fr_fixed, fixed_f);
@@ -518,9 +464,7 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
         CU(cudaMemcpyAsync(p->d_und_b.p, ub.data(), ub.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
         CU(cudaStreamSynchronize(p->stream));
     }
-    { const char *e = getenv("AAR_DEBUG_MARKERS"); if (e && *e == '1') { CU(cudaHostAlloc((void **)&p->h_dbg, 8 * 256 * sizeof(int), cudaHostAllocMapped)); std::memset(p->h_dbg, 0, 8 * 256 * sizeof(int)); int *dptr = nullptr; CU(cudaHostGetDevicePointer((void **)&dptr, p->h_dbg, 0)); p->dp.dbg = dptr; } }
     { const char *e = getenv("AAR_FORCE_EXACT_STAGING"); p->force_exact_staging = e && *e == '1'; }   // test hook: FP64 staging of the Jacobian block
-    { int rc = build_jac_plan(p, p->force_exact_staging ? p->plan_f64 : p->plan_f32, p->force_exact_staging); if (rc) return rc; }
     if (schur_smem(p) > 48 * 1024) {
         if (schur_smem(p) > 227 * 1024) { set_err("frame sees too many blocks for the Schur kernel"); return AAR_ERR_UNSUPPORTED; }
         CU(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(p)));
@@ -797,7 +741,8 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
                 float ms;
                 if (ntries == 0) {
                     cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms;
-                    cudaEventElapsedTime(&ms, p->ev[7], p->ev[8]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+                    cudaEventElapsedTime(&ms, p->ev[7], p->ev[9]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+                    cudaEventElapsedTime(&ms, p->ev[9], p->ev[8]); p->phase_ms[7] += ms;
                 }
                 cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
                 cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;

@@ -35,7 +35,6 @@ struct DevProblem {
     double *cam_tab, *mk_tab, *fr_tab;
     double *cam_tr, *mk_tr, *fr_tr; // trial (z + delta) tables, base only: [.][12]
     const double *cam_fixed, *mk_fixed, *fr_fixed; // host matrices [.][12] for non-optimised groups
-    volatile int *dbg;           // development aid: per-warp progress markers in mapped host memory (NULL normally)
 };
 
 __device__ __forceinline__ int obs_cam(int cm) { return cm & 0xfff; }

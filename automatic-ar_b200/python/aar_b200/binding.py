@@ -246,9 +246,9 @@ class Problem:
         _chk(lib().aar_set_profiling(self.h, C.c_int32(int(on))), "aar_set_profiling")
 
     def phase_ms(self):
-        v = (C.c_double * 7)()
+        v = (C.c_double * 8)()
         _chk(lib().aar_get_phase_ms(self.h, v), "aar_get_phase_ms")
-        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm", "jacobian_kernel", "jacobian_launches"], list(v)))
+        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm", "jacobian_kernel", "jacobian_launches", "accumulate_kernel"], list(v)))
 
 
 def comm_unique_id() -> bytes:

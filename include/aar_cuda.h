@@ -150,8 +150,9 @@ int aar_comm_init(aar_problem *p, const void *id128);
 /* instrumentation for bench.py: kernels launched by this handle so far, and device time (ms, CUDA events on
  * the handle's stream) accumulated per phase since aar_set_profiling(p, 1):
  *   [0] expansion + Jacobian/normal-equation assembly  [1] Schur + all-reduce + reduced solve  [2] back-substitution
- *   [3] trial residual  [4] cost all-reduce + decision  [5] the Jacobian kernel alone  [6] number of Jacobian launches in [5] */
-#define AAR_NUM_PHASES 7
+ *   [3] trial residual  [4] cost all-reduce + decision  [5] k_jac_project alone  [6] number of launches in [5]
+ *   [7] k_jac_accumulate alone */
+#define AAR_NUM_PHASES 8
 int64_t aar_kernel_launches(const aar_problem *p);
 int aar_set_profiling(aar_problem *p, int32_t on);
 int aar_get_phase_ms(const aar_problem *p, double *ms /* [AAR_NUM_PHASES] */);
