@@ -92,7 +92,8 @@ struct aar_problem {
     cudaStream_t stream = nullptr; bool own_stream = false;
     DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
-    DevBuf<int> d_frame_cs_cum;
+    DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot;
+    DevBuf<double> d_fc, d_E;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
     DevBuf<LmState> d_st;
@@ -227,19 +228,37 @@ __global__ void k_prepare_reduced(int n_r, const double *__restrict__ Hrr, const
     else if (e < nn + n_r) { double v = -gr[e - nn]; red[e] = v; red[e + n_r] = v; }
 }
 
-size_t schur_smem(const aar_problem *p) { return (size_t)SCHUR_WARPS * std::max(p->max_slots, 1) * 36 * sizeof(double); }
+// Schur elimination of the frame blocks of this rank into S (must hold Hrr) and b (must hold -gr)
+int schur_eliminate(aar_problem *p, double *S, double *b) {
+    const int n_r = p->n_r, nb = p->nrc + p->nrm, F = p->dp.F;
+    if (!p->opt_f || F <= 0 || n_r <= 0) return AAR_OK;
+    LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);
+    if (p->nslots > 0) {
+        const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots * 6 + 255) / 256));
+        LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
+        const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
+        const int nchunks = std::max(1, std::min((2 * p->num_sms + ntiles - 1) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
+        LAUNCH(p, k_schur_syrk, ntiles * nchunks, SY_THREADS, SY_SMEM, p->dp, nb, tiles_side, nchunks, p->d_frame_block_slot.p, p->d_E.p, S);
+    }
+    return AAR_OK;
+}
 
 // one try of the do-while of SparseLevMarq::step (sparselevmarq.h:384-419) up to (not including) the decision
 int build_and_solve_reduced(aar_problem *p) {
     const int n_r = p->n_r;
     double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
     if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, S);
-    if (p->opt_f && p->dp.F > 0 && n_r > 0)
-        LAUNCH(p, k_schur, cdiv(p->dp.F, SCHUR_WARPS), SCHUR_WARPS * 32, schur_smem(p), p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, S, b, std::max(p->max_slots, 1), p->d_flag.p);
+    { int rc = schur_eliminate(p, S, b); if (rc) return rc; }
     if (n_r > 0) {
         int rc = allreduce(p, S, (size_t)n_r * n_r + 2 * n_r, ncclSum);
         if (rc) return rc;
-        LAUNCH(p, k_reduced_solve, 1, 1024, 0, n_r, S, b, p->d_dr.p, p->d_st.p, p->d_flag.p);
+        {   // cooperative launch: one CTA per block row of 32 (all co-resident: n_r / 32 <= number of SMs)
+            int n = n_r; double *xs = p->d_dr.p; const LmState *stp = p->d_st.p; int *fl = p->d_flag.p; const double *bb = b;
+            void *args[] = {&n, &S, &bb, &xs, &stp, &fl};
+            const int gridc = std::max(1, std::min((n_r + CH_NB - 1) / CH_NB, p->num_sms));
+            CU(cudaLaunchCooperativeKernel((const void *)k_reduced_solve, dim3(gridc), dim3(CH_THREADS), args, 0, p->stream));
+            p->launches++;
+        }
         LAUNCH(p, k_apply_reduced, cdiv(n_r, 128), 128, 0, n_r, p->d_z.p, p->d_dr.p, p->d_zt.p);
     }
     (void)Br;
@@ -381,6 +400,9 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
         }
     }
     p->nslots = (long long)slot_block.size();
+    std::vector<int> slot_frame((size_t)p->nslots), frame_block_slot((size_t)std::max(Fl, 1) * std::max(p->nrc + p->nrm, 1), -1);
+    for (int f = 0; f < Fl; f++)
+        for (int sl = slot_ptr[(size_t)f]; sl < slot_ptr[(size_t)f + 1]; sl++) { slot_frame[(size_t)sl] = f; frame_block_slot[(size_t)f * (p->nrc + p->nrm) + slot_block[(size_t)sl]] = sl; }
 
     // ---- device
     int ndev = 0;
@@ -415,6 +437,7 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     do { CU((buf).alloc((vec).size())); if ((vec).size()) CU(cudaMemcpyAsync((buf).p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream)); } while (0)
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
     UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block); UP(p->d_frame_cs_cum, cs_cum);
+    UP(p->d_slot_frame, slot_frame); UP(p->d_frame_block_slot, frame_block_slot);
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
     UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
@@ -425,6 +448,7 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     CU(p->d_cam_tr.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_mk_tr.alloc((size_t)p->M * POSE_STRIDE)); CU(p->d_fr_tr.alloc((size_t)std::max(Fl, 1) * POSE_STRIDE));
     const size_t nz = (size_t)std::max<long long>(p->n_vars, 1);
     CU(p->d_z.alloc(nz)); CU(p->d_zt.alloc(nz)); CU(p->d_z0.alloc(nz));
+    CU(p->d_fc.alloc((size_t)std::max(Fl, 1) * FC_STRIDE)); CU(p->d_E.alloc((size_t)std::max<long long>(p->nslots, 1) * 36));
     CU(p->d_Hf.alloc((size_t)std::max(Fl, 1) * HF_STRIDE)); CU(p->d_W.alloc((size_t)std::max<long long>(p->nslots, 1) * 36));
     CU(p->d_Hrr.alloc((size_t)std::max(p->n_r, 1) * std::max(p->n_r, 1))); CU(p->d_gr.alloc((size_t)std::max(p->n_r, 1)));
     CU(p->d_red.alloc((size_t)p->n_r * p->n_r + 2 * (size_t)p->n_r + 8)); CU(p->d_dr.alloc((size_t)std::max(p->n_r, 1)));
@@ -465,10 +489,8 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
         CU(cudaStreamSynchronize(p->stream));
     }
     { const char *e = getenv("AAR_FORCE_EXACT_STAGING"); p->force_exact_staging = e && *e == '1'; }   // test hook: FP64 staging of the Jacobian block
-    if (schur_smem(p) > 48 * 1024) {
-        if (schur_smem(p) > 227 * 1024) { set_err("frame sees too many blocks for the Schur kernel"); return AAR_ERR_UNSUPPORTED; }
-        CU(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem(p)));
-    }
+    CU(cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    if ((size_t)p->n_r * sizeof(double) > 48 * 1024) CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)p->n_r * sizeof(double))));
     CU(cudaStreamSynchronize(p->stream));
     aar_lm_default_params(&p->params);
     guard.release();
@@ -642,8 +664,7 @@ int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, do
     const int n_r = p->n_r;
     double *dS = p->d_red.p;
     if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, dS);
-    if (p->opt_f && p->dp.F > 0 && n_r > 0)
-        LAUNCH(p, k_schur, cdiv(p->dp.F, SCHUR_WARPS), SCHUR_WARPS * 32, schur_smem(p), p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, dS, dS + (size_t)n_r * n_r, std::max(p->max_slots, 1), p->d_flag.p);
+    if ((rc = schur_eliminate(p, dS, dS + (size_t)n_r * n_r))) return rc;
     if (S && n_r) CU(cudaMemcpyAsync(S, dS, (size_t)n_r * n_r * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (b && n_r) CU(cudaMemcpyAsync(b, dS + (size_t)n_r * n_r, (size_t)n_r * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(p->h_red3, p->d_red3.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));

@@ -232,112 +232,6 @@ __device__ __forceinline__ void bwd6(const double *L, double *x) {
     }
 }
 
-// Schur elimination of the frame blocks (replaces the sparse LDLT of sparselevmarq.h:394-400 on the
-// arrow-shaped JtJ): one warp per frame.
-//   D = Hff + mu I = L L^T ; E_s = W_s L^-T ; y = L^-1 Bf (Bf = -gf)
-//   S[bs,bt] -= E_s E_t^T (upper block triangle) ; b[bs] -= E_s y
-// S must hold Hrr (without mu) on entry, b must hold Br = -gr.
-constexpr int SCHUR_WARPS = 4;
-__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevProblem p, const LmState *__restrict__ st, const double *__restrict__ Hf, const double *__restrict__ W,
-                                                            double *__restrict__ S, double *__restrict__ b, int max_slots, int *__restrict__ chol_fail) {
-    extern __shared__ double sE[]; // [SCHUR_WARPS][max_slots][36]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int f = blockIdx.x * SCHUR_WARPS + wid;
-    if (f >= p.F) return;
-    const double mu = st->mu;
-    double L[36];
-    if (!chol6(Hf + (size_t)f * HF_STRIDE, mu, L) && lane == 0) atomicExch(chol_fail, 1);
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) y[i] = -Hf[(size_t)f * HF_STRIDE + 21 + i];
-    fwd6(L, y);
-    const int s0 = p.frame_slot_ptr[f], ns = p.frame_slot_ptr[f + 1] - s0;
-    double *E = sE + (size_t)wid * max_slots * 36;
-    const int n_r = p.n_r;
-    for (int s = lane; s < ns; s += 32) {
-        const double *w = W + (size_t)(s0 + s) * 36;
-        const int bs = 6 * p.slot_block[s0 + s];
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            double row[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) row[k] = w[i * 6 + k];
-            fwd6(L, row); // e^T = L^-1 w^T
-            double acc = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) { E[s * 36 + i * 6 + k] = row[k]; acc = fma(row[k], y[k], acc); }
-            atomicAdd(b + bs + i, -acc);
-        }
-    }
-    __syncwarp();
-    const int npairs = ns * (ns + 1) / 2;
-    for (int q = lane; q < npairs; q += 32) {
-        // unrank q -> (s <= t)
-        int s = 0, rem = q;
-        while (rem >= ns - s) { rem -= ns - s; s++; }
-        int t = s + rem;
-        int bs = 6 * p.slot_block[s0 + s], bt = 6 * p.slot_block[s0 + t];
-        const double *Es = E + s * 36, *Et = E + t * 36;
-        if (bs > bt) { int tmp = bs; bs = bt; bt = tmp; const double *tp = Es; Es = Et; Et = tp; }
-        for (int i = 0; i < 6; i++)
-            for (int j = 0; j < 6; j++) {
-                double acc = 0;
-#pragma unroll
-                for (int k = 0; k < 6; k++) acc = fma(Es[i * 6 + k], Et[j * 6 + k], acc);
-                atomicAdd(S + (size_t)(bs + i) * n_r + bt + j, -acc);
-            }
-    }
-}
-
-// Dense Cholesky solve of the reduced system (S + mu I) x = b, one CTA, upper triangle of S is valid.
-// Works in place in global memory (S is overwritten with the factor). n_r <= a few hundred.
-__global__ void __launch_bounds__(1024) k_reduced_solve(int n, double *__restrict__ S, const double *__restrict__ b, double *__restrict__ x, const LmState *__restrict__ st, int *__restrict__ chol_fail) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const double mu = st->mu;
-    __shared__ double sdiag;
-    // symmetrise: copy upper to lower, add mu
-    for (int e = tid; e < n * n; e += nt) { int i = e / n, j = e % n; if (i > j) S[e] = S[(size_t)j * n + i]; }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) S[(size_t)i * n + i] += mu;
-    __syncthreads();
-    // right-looking Cholesky, lower factor stored in the lower triangle
-    for (int j = 0; j < n; j++) {
-        if (tid == 0) { double d = S[(size_t)j * n + j]; if (!(d > 0)) { atomicExch(chol_fail, 1); d = 1; } sdiag = sqrt(d); S[(size_t)j * n + j] = sdiag; }
-        __syncthreads();
-        const double inv = 1.0 / sdiag;
-        for (int i = j + 1 + tid; i < n; i += nt) S[(size_t)i * n + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: S[i][k] -= L[i][j]*L[k][j], j < k <= i
-        const int rem = n - j - 1;
-        for (int e = tid; e < rem * rem; e += nt) {
-            int i = j + 1 + e / rem, k = j + 1 + e % rem;
-            if (k <= i) S[(size_t)i * n + k] = fma(-S[(size_t)i * n + j], S[(size_t)k * n + j], S[(size_t)i * n + k]);
-        }
-        __syncthreads();
-    }
-    // forward / backward substitution (single warp, serial over rows, parallel dot products)
-    for (int i = tid; i < n; i += nt) x[i] = b[i];
-    __syncthreads();
-    if (tid < 32) {
-        for (int i = 0; i < n; i++) {
-            double s = 0;
-            for (int k = tid; k < i; k += 32) s = fma(S[(size_t)i * n + k], x[k], s);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
-            __syncwarp();
-        }
-        for (int i = n - 1; i >= 0; i--) {
-            double s = 0;
-            for (int k = i + 1 + tid; k < n; k += 32) s = fma(S[(size_t)k * n + i], x[k], s);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
-            __syncwarp();
-        }
-    }
-}
-
 // Back-substitution delta_f = D^-1 (Bf - W_f^T delta_r) (one thread per frame), trial point z + delta,
 // and the frame part of the two dot products needed by L = 1/2 delta^T (mu delta - B) (sparselevmarq.h:406).
 __global__ void k_backsub(DevProblem p, const LmState *__restrict__ st, const double *__restrict__ Hf, const double *__restrict__ W, const double *__restrict__ dr,
@@ -454,3 +348,6 @@ __global__ void k_undistort(long long n4, const float2 *__restrict__ in, const i
 }
 
 } // namespace aar
+
+#include "aar_schur.cuh"
+#include "aar_dense.cuh"
