@@ -176,7 +176,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     (void)attr_done;
     const long long N = p->dp.N;
     const int grid1 = (int)std::max<long long>(1, std::min<long long>(2LL * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
-    const int per_sm2 = smem2 <= 110 * 1024 ? 2 : 1;
+    const int per_sm2 = 1;   // 255 registers per thread: the whole 8x18 block of an observation lives in registers
     const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm2 * p->num_sms, (N + ACC_WARPS * 32 - 1) / (ACC_WARPS * 32)));
     prof_mark(p, 7);
     k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p);
@@ -237,7 +237,8 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
         const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots * 6 + 255) / 256));
         LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
-        const int nchunks = std::max(1, std::min((2 * p->num_sms + ntiles - 1) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
+        // two CTAs per SM, at most two full waves (no tail wave), at least a few pipeline stages per CTA
+        const int nchunks = std::max(1, std::min((4 * p->num_sms) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
         LAUNCH(p, k_schur_syrk, ntiles * nchunks, SY_THREADS, SY_SMEM, p->dp, nb, tiles_side, nchunks, p->d_frame_block_slot.p, p->d_E.p, S);
     }
     return AAR_OK;

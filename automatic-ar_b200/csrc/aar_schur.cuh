@@ -17,9 +17,9 @@ namespace aar {
 constexpr int FC_STRIDE = 28;      // per frame: L (lower, packed by rows, 21) | y (6) | pad
 constexpr int SY_TB = 16;          // 6x6 blocks per tile side
 constexpr int SY_LD = 37;          // padded block stride in shared memory (conflict-free 64-bit loads across blocks)
-constexpr int SY_FB = 6;           // frames per staged batch
+constexpr int SY_FB = 4;           // frames per pipeline stage
 constexpr int SY_THREADS = 256;
-constexpr size_t SY_SMEM = sizeof(double) * 2 * SY_FB * SY_TB * SY_LD + sizeof(int) * 2 * SY_FB * SY_TB;
+constexpr size_t SY_SMEM = 2 * (sizeof(double) * 2 * SY_FB * SY_TB * SY_LD + sizeof(int) * 2 * SY_FB * SY_TB);   // two stages
 
 // D = Hff + mu I = L L^T, y = L^-1 (-gf).  Non-positive pivot -> chol_fail (the reference does not check its LDLT,
 // sparselevmarq.h:394-400; the host treats it as a rejected step).
@@ -74,11 +74,21 @@ __global__ void __launch_bounds__(256) k_schur_prepare(DevProblem p, long long n
 
 // S[tile] -= sum over the frames of this chunk of E_I E_J^T.  frame_block_slot[f*nb + blk] is the W slot of
 // reduced block blk in frame f, or -1.  gridDim.x = ntiles * nchunks (tile fastest).
-__global__ void __launch_bounds__(SY_THREADS, 1) k_schur_syrk(DevProblem p, int nb, int tiles_side, int nchunks, const int *__restrict__ frame_block_slot,
+// Software pipeline over batches of SY_FB frames: slot indices are fetched two batches ahead (registers), the E
+// blocks one batch ahead (cp.async into the other shared-memory buffer, zero-filled for absent blocks), so the
+// FP64 FMAs of batch b overlap the global-memory latency of batches b+1 and b+2.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(SY_THREADS, 2) k_schur_syrk(DevProblem p, int nb, int tiles_side, int nchunks, const int *__restrict__ frame_block_slot,
                                                               const double *__restrict__ E, double *__restrict__ S) {
     extern __shared__ __align__(16) unsigned char sy_raw[];
-    double (*sE)[SY_FB][SY_TB * SY_LD] = reinterpret_cast<double (*)[SY_FB][SY_TB * SY_LD]>(sy_raw);            // [I|J][frame in batch][block][36 (+1)]
-    int (*sPresent)[SY_FB][SY_TB] = reinterpret_cast<int (*)[SY_FB][SY_TB]>(sy_raw + sizeof(double) * 2 * SY_FB * SY_TB * SY_LD);
+    typedef double EBuf[2][SY_FB][SY_TB * SY_LD];          // [I|J][frame in batch][block][36 (+1)]
+    typedef int PBuf[2][SY_FB][SY_TB];
+    EBuf *sE = reinterpret_cast<EBuf *>(sy_raw);             // two pipeline stages
+    PBuf *sPresent = reinterpret_cast<PBuf *>(sy_raw + 2 * sizeof(EBuf));
     const int ntiles = tiles_side * (tiles_side + 1) / 2;
     int tile = blockIdx.x % ntiles; const int chunk = blockIdx.x / ntiles;
     int ti = 0;
@@ -88,29 +98,46 @@ __global__ void __launch_bounds__(SY_THREADS, 1) k_schur_syrk(DevProblem p, int 
     const int f0 = (int)((long long)p.F * chunk / nchunks), f1 = (int)((long long)p.F * (chunk + 1) / nchunks);
     const int gi = ti * SY_TB + bi, gj = tj * SY_TB + bj;                    // global block indices of this thread's pair
     const bool mine = gi < nb && gj < nb && (ti != tj || bi <= bj);          // upper block triangle only
+    const int nbatch = (f1 - f0 + SY_FB - 1) / SY_FB;
+    // slot-index prefetch: thread e < 2*SY_FB*SY_TB owns entry (side, ff, blk) of every batch
+    const bool idx_thread = tid < 2 * SY_FB * SY_TB;
+    const int i_side = tid / (SY_FB * SY_TB), i_ff = (tid / SY_TB) % SY_FB, i_blk = tid % SY_TB;
+    const int i_g = (i_side ? tj : ti) * SY_TB + i_blk;
+    auto fetch_slot = [&](int batch) -> int {
+        const int f = f0 + batch * SY_FB + i_ff;
+        return (idx_thread && batch < nbatch && f < f1 && i_g < nb) ? frame_block_slot[(size_t)f * nb + i_g] : -1;
+    };
+    auto issue_copy = [&](int stage) {      // E blocks of the batch whose slots are in sPresent[stage]
+        double *dst0 = &sE[stage][0][0][0]; const int *pres = &sPresent[stage][0][0][0];
+        for (int e = tid; e < 2 * SY_FB * SY_TB * 36; e += SY_THREADS) {
+            const int k = e % 36, blkid = e / 36;            // blkid = (side*SY_FB + ff)*SY_TB + blk
+            const int slot = pres[blkid];
+            cp_async8(dst0 + (size_t)blkid * SY_LD + k, E + (size_t)(slot >= 0 ? slot : 0) * 36 + k, slot >= 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     double acc[36];
 #pragma unroll
     for (int i = 0; i < 36; i++) acc[i] = 0.0;
-    for (int fb0 = f0; fb0 < f1; fb0 += SY_FB) {
-        const int nf = min(SY_FB, f1 - fb0);
+    // prologue: slots of batch 0 -> shared, copy of batch 0 in flight, slots of batch 1 in registers
+    int slot_next = fetch_slot(0);
+    if (idx_thread) (&sPresent[0][0][0][0])[tid] = slot_next;
+    slot_next = fetch_slot(1);
+    __syncthreads();
+    issue_copy(0);
+    for (int b = 0; b < nbatch; b++) {
+        const int cur = b & 1, nxt = cur ^ 1;
+        if (idx_thread) (&sPresent[nxt][0][0][0])[tid] = slot_next;        // slots of batch b+1
+        slot_next = fetch_slot(b + 2);
         __syncthreads();
-        // stage: 2 sides x nf frames x 16 blocks x 36 doubles
-        for (int e = tid; e < 2 * nf * SY_TB; e += SY_THREADS) {
-            const int side = e / (nf * SY_TB), rem = e % (nf * SY_TB), ff = rem / SY_TB, blk = rem % SY_TB;
-            const int g = (side ? tj : ti) * SY_TB + blk;
-            sPresent[side][ff][blk] = g < nb ? frame_block_slot[(size_t)(fb0 + ff) * nb + g] : -1;
-        }
-        __syncthreads();
-        for (int e = tid; e < 2 * nf * SY_TB * 36; e += SY_THREADS) {
-            const int k = e % 36, rem = e / 36, side = rem / (nf * SY_TB), rem2 = rem % (nf * SY_TB), ff = rem2 / SY_TB, blk = rem2 % SY_TB;
-            const int slot = sPresent[side][ff][blk];
-            sE[side][ff][blk * SY_LD + k] = slot >= 0 ? E[(size_t)slot * 36 + k] : 0.0;
-        }
+        if (b + 1 < nbatch) { issue_copy(nxt); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         if (mine) {
+            const int nf = min(SY_FB, f1 - (f0 + b * SY_FB));
             for (int ff = 0; ff < nf; ff++) {
-                if (sPresent[0][ff][bi] < 0 || sPresent[1][ff][bj] < 0) continue;
-                const double *ei = &sE[0][ff][bi * SY_LD], *ej = &sE[1][ff][bj * SY_LD];
+                if (sPresent[cur][0][ff][bi] < 0 || sPresent[cur][1][ff][bj] < 0) continue;
+                const double *ei = &sE[cur][0][ff][bi * SY_LD], *ej = &sE[cur][1][ff][bj * SY_LD];
                 double a[36];
 #pragma unroll
                 for (int i = 0; i < 36; i++) a[i] = ei[i];
@@ -129,6 +156,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) k_schur_syrk(DevProblem p, int 
                 }
             }
         }
+        __syncthreads();
     }
     if (mine) {
         double *dst = S + (size_t)(6 * gi) * p.n_r + 6 * gj;
