@@ -288,7 +288,7 @@ void aar_lm_default_params(aar_lm_params *q) {
     q->tau = 1; q->der_epsilon = 1e-3; q->ignore_stop_rules = 0; q->verbose = 0;
 }
 
-int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
+static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_only) {
     if (!d || !out) { set_err("null argument"); return AAR_ERR_INVALID; }
     *out = nullptr;
     if (d->optimize_cam_intrinsics) { set_err("optimize_cam_intrinsics is not supported by the device path (SURVEY 8f row 4)"); return AAR_ERR_UNSUPPORTED; }
@@ -405,6 +405,7 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     for (int f = 0; f < Fl; f++)
         for (int sl = slot_ptr[(size_t)f]; sl < slot_ptr[(size_t)f + 1]; sl++) { slot_frame[(size_t)sl] = f; frame_block_slot[(size_t)f * (p->nrc + p->nrm) + slot_block[(size_t)sl]] = sl; }
 
+    if (host_only) { guard.release(); *out = p; return AAR_OK; }   // aar_shard_plan: row map and shard only
     // ---- device
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device: the B200 path has no CPU fallback"); return AAR_ERR_CUDA; }
@@ -499,8 +500,21 @@ int aar_problem_create(const aar_problem_desc *d, aar_problem **out) {
     return AAR_OK;
 }
 
+int aar_problem_create(const aar_problem_desc *d, aar_problem **out) { return create_impl(d, out, false); }
+
+int aar_shard_plan(const aar_problem_desc *d, int32_t *frame_begin, int32_t *frame_end, int64_t *obs_begin, int64_t *obs_end, int64_t *num_observations) {
+    aar_problem *p = nullptr;
+    int rc = create_impl(d, &p, true);
+    if (rc) return rc;
+    if (frame_begin) *frame_begin = p->f_begin; if (frame_end) *frame_end = p->f_end;
+    if (obs_begin) *obs_begin = p->o_begin; if (obs_end) *obs_end = p->o_end; if (num_observations) *num_observations = p->N;
+    delete p;
+    return AAR_OK;
+}
+
 void aar_problem_destroy(aar_problem *p) {
     if (!p) return;
+    if (!p->stream && !p->h_st) { delete p; return; }   // host-only handle
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);

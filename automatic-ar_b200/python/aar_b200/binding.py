@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 EXPORTS = ["aar_lm_default_params", "aar_problem_create", "aar_problem_destroy", "aar_last_error", "aar_num_vars",
            "aar_num_observations", "aar_num_local_observations", "aar_jacobian_nnz", "aar_index_maps", "aar_get_observations",
            "aar_mats2evec", "aar_evec2mats", "aar_eval_residual", "aar_eval_jacobian", "aar_reduced_system", "aar_lm_solve",
-           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_comm_unique_id", "aar_comm_init",
+           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_shard_plan", "aar_comm_unique_id", "aar_comm_init",
            "aar_kernel_launches", "aar_set_profiling", "aar_get_phase_ms"]
 
 
@@ -104,10 +104,17 @@ def _vp(a):
 class Problem:
     """MultiCamMapper-shaped handle on one GPU (one rank's frame shard when world_size > 1)."""
 
-    def __init__(self, rig, use_init=True, cams=True, markers=True, objects=True, with_huber=False, device=0, stream=None,
-                 rank=0, world_size=1, J_delta=0.0):
-        L = lib()
-        k = self._keep = {}
+    @staticmethod
+    def shard_plan(rig, rank, world_size):
+        """aar_shard_plan: (frame_begin, frame_end, obs_begin, obs_end, num_observations) of a rank, host only."""
+        d, keep = Problem._desc(rig, True, True, True, True, False, 0, None, rank, world_size, 0.0)
+        fb = C.c_int32(0); fe = C.c_int32(0); ob = C.c_int64(0); oe = C.c_int64(0); n = C.c_int64(0)
+        _chk(lib().aar_shard_plan(C.byref(d), C.byref(fb), C.byref(fe), C.byref(ob), C.byref(oe), C.byref(n)), "aar_shard_plan")
+        return fb.value, fe.value, ob.value, oe.value, n.value
+
+    @staticmethod
+    def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta):
+        k = {}
         k["cam_ids"] = np.ascontiguousarray(rig.cam_ids, np.int32); k["marker_ids"] = np.ascontiguousarray(rig.marker_ids, np.int32)
         k["frame_ids"] = np.ascontiguousarray(rig.frame_ids, np.int32)
         k["cam_T"] = np.ascontiguousarray(rig.T_cam_init if use_init else rig.T_cam_true, np.float64)
@@ -127,6 +134,12 @@ class Problem:
         d.with_huber = int(with_huber); d.J_delta = J_delta; d.device = device
         d.stream = C.c_void_p(stream) if stream else None
         d.rank, d.world_size = rank, world_size
+        return d, k
+
+    def __init__(self, rig, use_init=True, cams=True, markers=True, objects=True, with_huber=False, device=0, stream=None,
+                 rank=0, world_size=1, J_delta=0.0):
+        L = lib()
+        d, self._keep = self._desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta)
         self.h = C.c_void_p()
         _chk(L.aar_problem_create(C.byref(d), C.byref(self.h)), "aar_problem_create")
         self.nC, self.nM, self.nF = d.num_cams, d.num_markers, d.num_frames

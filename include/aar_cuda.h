@@ -143,6 +143,11 @@ int aar_lm_end(aar_problem *p, double *z_out);
  * (calcDerivates, sparselevmarq.h:164-220).  z6 [num_frames_local][6] in/out. */
 int aar_track_batch(aar_problem *p, double *z6_inout, const aar_lm_params *params, double *final_cost, int32_t *iterations);
 
+/* The frame shard a handle created from `desc` (rank, world_size) would own, computed on the host without touching a
+ * device: contiguous frame-index range [frame_begin, frame_end) balanced by observation count, and its observation
+ * (row / 8) range.  Any output pointer may be NULL. */
+int aar_shard_plan(const aar_problem_desc *desc, int32_t *frame_begin, int32_t *frame_end, int64_t *obs_begin, int64_t *obs_end, int64_t *num_observations);
+
 /* multi-GPU: one handle per rank; id is the 128-byte ncclUniqueId created on rank 0 */
 int aar_comm_unique_id(void *id128);
 int aar_comm_init(aar_problem *p, const void *id128);
