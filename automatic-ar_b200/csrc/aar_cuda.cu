@@ -92,7 +92,8 @@ struct aar_problem {
     cudaStream_t stream = nullptr; bool own_stream = false;
     DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
-    DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot;
+    DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters;
+    DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
@@ -440,6 +441,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
     UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block); UP(p->d_frame_cs_cum, cs_cum);
     UP(p->d_slot_frame, slot_frame); UP(p->d_frame_block_slot, frame_block_slot);
+    { std::vector<int> fop((size_t)Fl + 1); for (int f = 0; f <= Fl; f++) fop[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin); UP(p->d_frame_obs_ptr, fop); }
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
     UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
@@ -842,9 +844,28 @@ int aar_lm_solve(aar_problem *p, double *z, const aar_lm_params *params, aar_lm_
     return aar_lm_end(p, z);
 }
 
-int aar_track_batch(aar_problem *, double *, const aar_lm_params *, double *, int32_t *) {
-    set_err("aar_track_batch: not built yet");
-    return AAR_ERR_UNSUPPORTED;
+int aar_track_batch(aar_problem *p, double *z6, const aar_lm_params *params, double *final_cost, int32_t *iterations) {
+    if (!p || !z6) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    aar_lm_params P; if (params) P = *params; else aar_lm_default_params(&P);
+    const int F = p->dp.F;
+    if (F == 0) return AAR_OK;
+    if (!p->d_trk_z.n) {
+        CU(p->d_trk_cam_inv.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_trk_Y.alloc((size_t)p->M * 12));
+        CU(p->d_trk_z.alloc((size_t)F * 6)); CU(p->d_trk_cost.alloc((size_t)F)); CU(p->d_trk_iters.alloc((size_t)F));
+    }
+    // the rig is the one the handle was created with (camera / marker transforms are not optimised by track())
+    LAUNCH(p, k_track_prepare, cdiv((long long)p->C + p->M, 128), 128, 0, p->dp, p->d_trk_cam_inv.p, p->d_trk_Y.p);
+    CU(cudaMemcpyAsync(p->d_trk_z.p, z6, (size_t)F * 6 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TrackParams tp; tp.max_iters = P.max_iters; tp.min_error = P.min_error; tp.min_step_error_diff = P.min_step_error_diff;
+    tp.min_average_step_error_diff = P.min_average_step_error_diff; tp.tau = P.tau; tp.der_epsilon = P.der_epsilon; tp.huber = p->huber;
+    LAUNCH(p, k_track, cdiv(F, TRK_WARPS), TRK_WARPS * 32, 0, p->dp, tp, p->d_frame_obs_ptr.p, p->d_trk_cam_inv.p, p->d_trk_Y.p, p->d_trk_z.p, p->d_trk_cost.p, p->d_trk_iters.p);
+    CU(cudaMemcpyAsync(z6, p->d_trk_z.p, (size_t)F * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (final_cost) CU(cudaMemcpyAsync(final_cost, p->d_trk_cost.p, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (iterations) CU(cudaMemcpyAsync(iterations, p->d_trk_iters.p, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    return AAR_OK;
 }
 
 int aar_comm_unique_id(void *id128) {

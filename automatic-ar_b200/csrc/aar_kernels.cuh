@@ -351,3 +351,4 @@ __global__ void k_undistort(long long n4, const float2 *__restrict__ in, const i
 
 #include "aar_schur.cuh"
 #include "aar_dense.cuh"
+#include "aar_track.cuh"

@@ -237,6 +237,14 @@ class Problem:
         _chk(lib().aar_lm_solve(self.h, _vp(z), C.byref(p), C.byref(rep)), "aar_lm_solve")
         return rep
 
+    def track_batch(self, z6, params=None):
+        """MultiCamMapper::track() for every frame of the handle: z6 [F_local, 6] -> (z6, final cost [F], iterations [F])."""
+        z = np.array(z6, np.float64, copy=True).reshape(-1, 6)
+        cost = np.zeros(len(z)); iters = np.zeros(len(z), np.int32)
+        p = params if params is not None else self.default_params()
+        _chk(lib().aar_track_batch(self.h, _vp(z), C.byref(p), _vp(cost), _vp(iters)), "aar_track_batch")
+        return z, cost, iters
+
     def lm_begin(self, z0=None, params=None):
         """z0 = None restarts from the z0 of the previous lm_begin (device resident, no copy)."""
         z = None if z0 is None else np.ascontiguousarray(z0, np.float64)
