@@ -475,7 +475,10 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
 
     // ---- remove_distortions (multicam_mapper.cpp:554-578) on the device: raw -> und.
     // raw_a/raw_b hold corners (0,1) / (2,3); run the point kernel on each half.
-    if (Nl > 0) {
+    if (Nl > 0 && d->corners_undistorted) {
+        CU(cudaMemcpyAsync(p->d_und_a.p, p->d_raw_a.p, (size_t)Nl * sizeof(float4), cudaMemcpyDeviceToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_und_b.p, p->d_raw_b.p, (size_t)Nl * sizeof(float4), cudaMemcpyDeviceToDevice, p->stream));
+    } else if (Nl > 0) {
         // view raw_a as 2*Nl float2 points whose observation is i>>1; reuse k_undistort with a shifted index map:
         // simplest is a temporary interleaved buffer of 4*Nl points in observation order.
         DevBuf<float2> tin, tout;

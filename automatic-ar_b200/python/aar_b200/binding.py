@@ -55,7 +55,7 @@ class Desc(C.Structure):
                 ("cam_T", C.c_void_p), ("marker_T", C.c_void_p), ("frame_T", C.c_void_p), ("cam_K", C.c_void_p), ("cam_dist", C.c_void_p),
                 ("num_detections", C.c_int64), ("det_frame", C.c_void_p), ("det_cam", C.c_void_p), ("det_marker", C.c_void_p), ("det_xy", C.c_void_p),
                 ("optimize_cam_poses", C.c_uint8), ("optimize_marker_poses", C.c_uint8), ("optimize_object_poses", C.c_uint8),
-                ("optimize_cam_intrinsics", C.c_uint8), ("with_huber", C.c_uint8), ("reserved", C.c_uint8 * 3),
+                ("optimize_cam_intrinsics", C.c_uint8), ("with_huber", C.c_uint8), ("corners_undistorted", C.c_uint8), ("reserved", C.c_uint8 * 2),
                 ("J_delta", C.c_double), ("device", C.c_int32), ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32)]
 
 

@@ -277,3 +277,84 @@ def write_dataset(folder, rig: Rig):
     os.makedirs(folder, exist_ok=True)
     write_calib_files(folder, rig)
     write_detections_file(os.path.join(folder, "aruco.detections"), rig)
+
+
+# ------------------------------------------------------------------ .solution files
+def rot2vec(R):
+    """(...,3,3) -> (...,3) rotation vectors (cv::Rodrigues matrix -> vector for proper rotations, angle < pi)."""
+    R = np.asarray(R, dtype=np.float64)
+    v = np.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], axis=-1)
+    s = np.linalg.norm(v, axis=-1) / 2
+    c = np.clip((np.trace(R, axis1=-2, axis2=-1) - 1) / 2, -1, 1)
+    th = np.arctan2(s, c)
+    k = np.where(s > 1e-12, th / np.maximum(2 * s, 1e-300), 0.5)
+    return v * k[..., None]
+
+
+def full_vector(rig: Rig, Tc, Tm, Tf):
+    """io_vec for the full Config: cams (root skipped), markers (root skipped), frames, per cam [fx cx fy cy k1 k2 p1 p2 k3]."""
+    def six(T):
+        return np.concatenate([rot2vec(T[:, :3, :3]), T[:, :3, 3]], axis=1).reshape(-1)
+    ci = rig.cam_ids != rig.root_cam; mi = rig.marker_ids != rig.root_marker
+    intr = np.concatenate([np.stack([rig.K[:, 0, 0], rig.K[:, 0, 2], rig.K[:, 1, 1], rig.K[:, 1, 2]], axis=1), rig.dist], axis=1).reshape(-1)
+    return np.concatenate([six(Tc[ci]), six(Tm[mi]), six(Tf), intr])
+
+
+def write_solution_file(path, rig: Rig, use_init=True, flags=(True, True, True, False)):
+    """The reference's binary .solution (libs/multicam_mapper.cpp:1053-1099).  Corners must already be undistorted:
+    only valid for rigs generated with distorted=False (undistortPoints with zero coefficients is the identity)."""
+    assert not np.any(rig.dist), "write_solution_file needs undistorted corners"
+    Tc, Tm, Tf = (rig.T_cam_init, rig.T_marker_init, rig.T_frame_init) if use_init else (rig.T_cam_true, rig.T_marker_true, rig.T_frame_true)
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<Q", rig.C)); fh.write(rig.cam_ids.astype("<i4").tobytes())
+        fh.write(struct.pack("<Q", int(rig.root_cam)))
+        for _ in range(rig.C):
+            fh.write(struct.pack("<ii", int(rig.image_size[0]), int(rig.image_size[1])))
+        fh.write(struct.pack("<Q", rig.M)); fh.write(rig.marker_ids.astype("<i4").tobytes())
+        fh.write(struct.pack("<Q", int(rig.root_marker)))
+        fh.write(struct.pack("<d", float(np.float32(rig.marker_size))))
+        fh.write(struct.pack("<Q", rig.F)); fh.write(rig.frame_ids.astype("<i4").tobytes())
+        fh.write(full_vector(rig, Tc, Tm, Tf).astype("<f8").tobytes())
+        # frame_cam_markers: frames ascending, cams ascending, detection order
+        order = np.lexsort((np.arange(rig.N), rig.det_cam, rig.det_frame))
+        df, dc, dm, xy = rig.det_frame[order], rig.det_cam[order], rig.det_marker[order], rig.det_xy[order]
+        frames, fstart = np.unique(df, return_index=True)
+        fh.write(struct.pack("<Q", len(frames)))
+        fend = list(fstart[1:]) + [len(df)]
+        rec = np.zeros(len(df), dtype=[("id", "<i4"), ("xy", "<f4", 8)]); rec["id"] = dm; rec["xy"] = xy
+        for f, a, b in zip(frames, fstart, fend):
+            cams, cstart = np.unique(dc[a:b], return_index=True)
+            fh.write(struct.pack("<iQ", int(f), len(cams)))
+            cend = list(cstart[1:]) + [b - a]
+            for c, ca, cb in zip(cams, cstart, cend):
+                fh.write(struct.pack("<iQ", int(c), cb - ca))
+                fh.write(rec[a + ca:a + cb].tobytes())
+        fh.write(struct.pack("<4?", *flags))
+
+
+def read_solution_file(path):
+    """-> dict(cam_ids, root_cam, image_sizes, marker_ids, root_marker, marker_size, frame_ids, vec, det_frame, det_cam, det_marker, det_xy, flags)"""
+    buf = open(path, "rb").read(); pos = 0
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from(fmt, buf, pos); pos += struct.calcsize(fmt); return v
+    C, = take("<Q"); cam_ids = np.frombuffer(buf, "<i4", C, pos).copy(); pos += 4 * C
+    root_cam, = take("<Q"); sizes = [take("<ii") for _ in range(C)]
+    M, = take("<Q"); marker_ids = np.frombuffer(buf, "<i4", M, pos).copy(); pos += 4 * M
+    root_marker, = take("<Q"); marker_size, = take("<d")
+    F, = take("<Q"); frame_ids = np.frombuffer(buf, "<i4", F, pos).copy(); pos += 4 * F
+    n = 6 * (C - 1) + 6 * (M - 1) + 6 * F + 9 * C
+    vec = np.frombuffer(buf, "<f8", n, pos).copy(); pos += 8 * n
+    nf, = take("<Q"); df, dc, dm, xy = [], [], [], []
+    for _ in range(nf):
+        f, nc = take("<iQ")
+        for _ in range(nc):
+            c, nm = take("<iQ")
+            rec = np.frombuffer(buf, [("id", "<i4"), ("xy", "<f4", 8)], nm, pos); pos += 36 * nm
+            df += [f] * nm; dc += [c] * nm; dm += list(rec["id"]); xy.append(rec["xy"].copy())
+    flags = take("<4?")
+    assert pos == len(buf)
+    return dict(cam_ids=cam_ids, root_cam=root_cam, image_sizes=sizes, marker_ids=marker_ids, root_marker=root_marker, marker_size=marker_size,
+                frame_ids=frame_ids, vec=vec, det_frame=np.array(df, np.int32), det_cam=np.array(dc, np.int32), det_marker=np.array(dm, np.int32),
+                det_xy=np.concatenate(xy) if xy else np.zeros((0, 8), np.float32), flags=flags)

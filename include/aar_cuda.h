@@ -55,7 +55,9 @@ typedef struct {
     /* MultiCamMapper::Config (multicam_mapper.h:75-81) + set_with_huber (:40) */
     uint8_t optimize_cam_poses, optimize_marker_poses, optimize_object_poses, optimize_cam_intrinsics;
     uint8_t with_huber;
-    uint8_t reserved[3];
+    uint8_t corners_undistorted;                      /* detections come from a .solution file (already undistorted, multicam_mapper.cpp:1085-1088):
+                                                       * no remove_distortions pass, and the Jacobian's "raw" corners are these corners too */
+    uint8_t reserved[2];
     double J_delta;                                   /* multicam_mapper.h:189, 0 -> 1e-3 */
     /* placement */
     int32_t device;                                   /* CUDA device ordinal */
