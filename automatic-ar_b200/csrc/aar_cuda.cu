@@ -94,7 +94,7 @@ struct aar_problem {
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters;
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
-    DevBuf<double> d_fc, d_E;
+    DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
     DevBuf<LmState> d_st;
@@ -169,15 +169,19 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT>;
     const size_t hcm_d = (size_t)p->nrc * p->nrm * 36;
     const size_t scr = (size_t)ACC_WARPS * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
-    AccPlan pl; pl.hcm_smem = fix + hcm_d * 8 + scr <= 100 * 1024; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
-    const size_t smem2 = fix + (pl.hcm_smem ? hcm_d * 8 : 0) + scr;
+    // as many camera x marker pair accumulators as the shared memory left over by the fixed part can hold
+    AccPlan pl; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
+    { const char *e = getenv("AAR_ACC_SKIP"); pl.skip = e ? atoi(e) : 0; }
+    const size_t room = p->smem_optin - 2048 > fix + scr ? p->smem_optin - 2048 - fix - scr : 0;
+    pl.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, room / 288);
+    const size_t smem2 = fix + (size_t)pl.hcm_smem * 288 + scr;
     if (smem2 > p->smem_optin - 1024) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     (void)attr_done;
     const long long N = p->dp.N;
     const int grid1 = (int)std::max<long long>(1, std::min<long long>(2LL * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
-    const int per_sm2 = 1;   // 255 registers per thread: the whole 8x18 block of an observation lives in registers
+    const int per_sm2 = smem2 * ACC_CTAS_PER_SM <= p->smem_optin ? ACC_CTAS_PER_SM : std::max<int>(1, (int)(p->smem_optin / smem2));
     const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm2 * p->num_sms, (N + ACC_WARPS * 32 - 1) / (ACC_WARPS * 32)));
     prof_mark(p, 7);
     k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p);
@@ -203,10 +207,11 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
         if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
         if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
         if (N == 0) return AAR_OK;
-        if (p->d_Rv.n < 8 * N) CU(p->d_Rv.alloc(8 * N));
+        const size_t Np = (N + 31) / 32 * 32;      // whole tiles of 32 observations
+        if (p->d_Rv.n < 8 * Np) CU(p->d_Rv.alloc(8 * Np));
         int rc;
-        if (exact) { if (p->d_Jn64.n < 144 * N) CU(p->d_Jn64.alloc(144 * N)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
-        else { if (p->d_Jn32.n < 144 * N) CU(p->d_Jn32.alloc(144 * N)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
+        if (exact) { if (p->d_Jn64.n < 144 * Np) CU(p->d_Jn64.alloc(144 * Np)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
+        else { if (p->d_Jn32.n < 144 * Np) CU(p->d_Jn32.alloc(144 * Np)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
         if (rc) return rc;
         if (exact) break;
         // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
@@ -256,7 +261,8 @@ int build_and_solve_reduced(aar_problem *p) {
         if (rc) return rc;
         {   // cooperative launch: one CTA per block row of 32 (all co-resident: n_r / 32 <= number of SMs)
             int n = n_r; double *xs = p->d_dr.p; const LmState *stp = p->d_st.p; int *fl = p->d_flag.p; const double *bb = b;
-            void *args[] = {&n, &S, &bb, &xs, &stp, &fl};
+            double *xinv = p->d_xinv.p;
+            void *args[] = {&n, &S, &bb, &xs, &stp, &fl, &xinv};
             const int gridc = std::max(1, std::min((n_r + CH_NB - 1) / CH_NB, p->num_sms));
             CU(cudaLaunchCooperativeKernel((const void *)k_reduced_solve, dim3(gridc), dim3(CH_THREADS), args, 0, p->stream));
             p->launches++;
@@ -456,6 +462,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     CU(p->d_Hf.alloc((size_t)std::max(Fl, 1) * HF_STRIDE)); CU(p->d_W.alloc((size_t)std::max<long long>(p->nslots, 1) * 36));
     CU(p->d_Hrr.alloc((size_t)std::max(p->n_r, 1) * std::max(p->n_r, 1))); CU(p->d_gr.alloc((size_t)std::max(p->n_r, 1)));
     CU(p->d_red.alloc((size_t)p->n_r * p->n_r + 2 * (size_t)p->n_r + 8)); CU(p->d_dr.alloc((size_t)std::max(p->n_r, 1)));
+    CU(p->d_xinv.alloc((size_t)((p->n_r + CH_NB - 1) / CH_NB + 1) * CH_NB * CH_NB));
     CU(p->d_red3.alloc(8)); CU(p->d_tmp.alloc((size_t)std::max(p->n_r, 1) + 8)); CU(p->d_st.alloc(1)); CU(p->d_flag.alloc(4));
     CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
     CU(cudaMemsetAsync(p->d_st.p, 0, sizeof(LmState), p->stream));

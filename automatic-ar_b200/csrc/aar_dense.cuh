@@ -4,8 +4,8 @@
 // shared memory, and on the critical path of every LM try.  Left-looking blocked factorisation, one CTA per block
 // row of 32, two grid-wide synchronisations per block column (cooperative launch):
 //   step k:  every CTA i >= k:  A_ik -= sum_{j<k} L_ij L_kj^T          (32x32x32 tile products from L2)
-//            CTA k:             L_kk = chol(A_kk)  in shared memory      -> grid sync
-//            every CTA i > k:   L_ik = A_ik L_kk^-T                      -> grid sync
+//            CTA k:             L_kk = chol(A_kk), X_k = L_kk^-1 in shared memory -> grid sync
+//            every CTA i > k:   L_ik = A_ik X_k^T   (a tile product, not a row-serial solve) -> grid sync
 // then forward / backward substitution by CTA 0.  S: row-major n x n, UPPER triangle valid on entry (the Schur
 // kernels only write the upper block triangle); the lower triangle holds L on exit.
 #pragma once
@@ -18,7 +18,7 @@ constexpr int CH_THREADS = 256;
 constexpr int CH_LD = CH_NB + 1;
 
 __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__restrict__ S, const double *__restrict__ b, double *__restrict__ x, const LmState *__restrict__ st,
-                                                              int *__restrict__ chol_fail) {
+                                                              int *__restrict__ chol_fail, double *__restrict__ Xinv /* [nblk][32][32] inverses of the diagonal factors */) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double sA[CH_NB * CH_LD], sB[CH_NB * CH_LD], sC[CH_NB * CH_LD];
@@ -76,6 +76,17 @@ __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__r
                     }
                     __syncthreads();
                 }
+                // X = L_kk^-1 (lower triangular): thread c < 32 solves L X[:, c] = e_c by forward substitution
+                if (tid < CH_NB) {
+                    const int c = tid;
+                    for (int r = 0; r < CH_NB; r++) {
+                        double v = r == c ? 1.0 : 0.0;
+                        for (int q = c; q < r; q++) v = fma(-sC[r * CH_LD + q], sB[q * CH_LD + c], v);
+                        sB[r * CH_LD + c] = r < c ? 0.0 : v / sC[r * CH_LD + r];
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) Xinv[(size_t)k * CH_NB * CH_NB + e] = sB[(e / CH_NB) * CH_LD + e % CH_NB];
             }
             // write the tile back (A_ik updated, or L_kk: lower triangle only)
             for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
@@ -84,28 +95,25 @@ __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__r
             }
         }
         grid.sync();
-        // ---- L_ik = A_ik L_kk^-T for i > k: one thread per row, forward substitution against L_kk
+        // ---- L_ik = A_ik X_k^T for i > k (X_k = L_kk^-1): L_ik[r][c] = sum_q A_ik[r][q] X_k[c][q]
         {
             bool loaded = false;
             for (int i = k + 1 + blockIdx.x; i < nblk; i += gridDim.x) {
-                if (!loaded) { __syncthreads(); load_tile(sB, k, k); loaded = true; }
                 __syncthreads();
+                if (!loaded) { for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sB[(e / CH_NB) * CH_LD + e % CH_NB] = Xinv[(size_t)k * CH_NB * CH_NB + e]; loaded = true; }
                 load_tile(sC, i, k);
                 __syncthreads();
-                if (tid < CH_NB) {
-                    double *row = sC + tid * CH_LD;
-                    for (int c = 0; c < CH_NB; c++) {
-                        double v = row[c];
-                        for (int q = 0; q < c; q++) v = fma(-row[q], sB[c * CH_LD + q], v);
-                        const double d = sB[c * CH_LD + c];
-                        row[c] = d != 0.0 ? v / d : 0.0;       // padding columns of the last block have no diagonal
-                    }
+                double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll 8
+                for (int q = 0; q < CH_NB; q++) {
+                    const double a0 = sC[ty * CH_LD + q], a1 = sC[(ty + 16) * CH_LD + q], b0 = sB[tx * CH_LD + q], b1 = sB[(tx + 16) * CH_LD + q];
+                    c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
                 }
-                __syncthreads();
-                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-                    const int r = e / CH_NB, c = e % CH_NB, gr = i * CH_NB + r, gc = k * CH_NB + c;
-                    if (gr < n && gc < n) S[(size_t)gr * n + gc] = sC[r * CH_LD + c];
-                }
+                const int gr0 = i * CH_NB + ty, gr1 = gr0 + 16, gc0 = k * CH_NB + tx, gc1 = gc0 + 16;
+                if (gr0 < n && gc0 < n) S[(size_t)gr0 * n + gc0] = c00;
+                if (gr0 < n && gc1 < n) S[(size_t)gr0 * n + gc1] = c01;
+                if (gr1 < n && gc0 < n) S[(size_t)gr1 * n + gc0] = c10;
+                if (gr1 < n && gc1 < n) S[(size_t)gr1 * n + gc1] = c11;
             }
         }
         grid.sync();
@@ -126,13 +134,14 @@ __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__r
             if (lane == 0) sv[r] = x[r0 + r] - s;
         }
         __syncthreads();
+        load_tile(sC, kb, kb);          // the diagonal factor, staged once (the solve below is latency bound)
+        __syncthreads();
         if (warp == 0) {   // 32x32 triangular solve, lane r owns row r
             double v = lane < nr ? sv[lane] : 0.0;
             for (int c = 0; c < nr; c++) {
-                const double d = S[(size_t)(r0 + c) * n + r0 + c];
-                const double xc = __shfl_sync(0xffffffffu, v, c) / d;
+                const double xc = __shfl_sync(0xffffffffu, v, c) / sC[c * CH_LD + c];
                 if (lane == c) v = xc;
-                else if (lane > c && lane < nr) v = fma(-S[(size_t)(r0 + lane) * n + r0 + c], xc, v);
+                else if (lane > c && lane < nr) v = fma(-sC[lane * CH_LD + c], xc, v);
             }
             if (lane < nr) x[r0 + lane] = v;
         }
@@ -148,13 +157,14 @@ __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__r
             if (lane == 0) sv[r] = x[r0 + r] - s;
         }
         __syncthreads();
+        load_tile(sC, kb, kb);
+        __syncthreads();
         if (warp == 0) {
             double v = lane < nr ? sv[lane] : 0.0;
             for (int c = nr - 1; c >= 0; c--) {
-                const double d = S[(size_t)(r0 + c) * n + r0 + c];
-                const double xc = __shfl_sync(0xffffffffu, v, c) / d;
+                const double xc = __shfl_sync(0xffffffffu, v, c) / sC[c * CH_LD + c];
                 if (lane == c) v = xc;
-                else if (lane < c) v = fma(-S[(size_t)(r0 + c) * n + r0 + lane], xc, v);
+                else if (lane < c) v = fma(-sC[c * CH_LD + lane], xc, v);
             }
             if (lane < nr) x[r0 + lane] = v;
         }

@@ -16,7 +16,7 @@ namespace aar {
 
 constexpr int FC_STRIDE = 28;      // per frame: L (lower, packed by rows, 21) | y (6) | pad
 constexpr int SY_TB = 16;          // 6x6 blocks per tile side
-constexpr int SY_LD = 37;          // padded block stride in shared memory (conflict-free 64-bit loads across blocks)
+constexpr int SY_LD = 38;          // padded block stride in shared memory: 16-byte aligned blocks, conflict-free 128-bit loads across blocks
 constexpr int SY_FB = 4;           // frames per pipeline stage
 constexpr int SY_THREADS = 256;
 constexpr size_t SY_SMEM = 2 * (sizeof(double) * 2 * SY_FB * SY_TB * SY_LD + sizeof(int) * 2 * SY_FB * SY_TB);   // two stages
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(256) k_schur_prepare(DevProblem p, long long n
 // Software pipeline over batches of SY_FB frames: slot indices are fetched two batches ahead (registers), the E
 // blocks one batch ahead (cp.async into the other shared-memory buffer, zero-filled for absent blocks), so the
 // FP64 FMAs of batch b overlap the global-memory latency of batches b+1 and b+2.
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 __global__ void __launch_bounds__(SY_THREADS, 2) k_schur_syrk(DevProblem p, int nb, int tiles_side, int nchunks, const int *__restrict__ frame_block_slot,
                                                               const double *__restrict__ E, double *__restrict__ S) {
@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_schur_syrk(DevProblem p, int 
     };
     auto issue_copy = [&](int stage) {      // E blocks of the batch whose slots are in sPresent[stage]
         double *dst0 = &sE[stage][0][0][0]; const int *pres = &sPresent[stage][0][0][0];
-        for (int e = tid; e < 2 * SY_FB * SY_TB * 36; e += SY_THREADS) {
-            const int k = e % 36, blkid = e / 36;            // blkid = (side*SY_FB + ff)*SY_TB + blk
+        for (int e = tid; e < 2 * SY_FB * SY_TB * 18; e += SY_THREADS) {
+            const int k = e % 18, blkid = e / 18;            // blkid = (side*SY_FB + ff)*SY_TB + blk ; 18 x 16 bytes per block
             const int slot = pres[blkid];
-            cp_async8(dst0 + (size_t)blkid * SY_LD + k, E + (size_t)(slot >= 0 ? slot : 0) * 36 + k, slot >= 0);
+            cp_async16(dst0 + (size_t)blkid * SY_LD + 2 * k, E + (size_t)(slot >= 0 ? slot : 0) * 36 + 2 * k, slot >= 0);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -137,15 +137,15 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_schur_syrk(DevProblem p, int 
             const int nf = min(SY_FB, f1 - (f0 + b * SY_FB));
             for (int ff = 0; ff < nf; ff++) {
                 if (sPresent[cur][0][ff][bi] < 0 || sPresent[cur][1][ff][bj] < 0) continue;
-                const double *ei = &sE[cur][0][ff][bi * SY_LD], *ej = &sE[cur][1][ff][bj * SY_LD];
+                const double2 *ei = reinterpret_cast<const double2 *>(&sE[cur][0][ff][bi * SY_LD]), *ej = reinterpret_cast<const double2 *>(&sE[cur][1][ff][bj * SY_LD]);
                 double a[36];
 #pragma unroll
-                for (int i = 0; i < 36; i++) a[i] = ei[i];
+                for (int i = 0; i < 18; i++) { const double2 v = ei[i]; a[2 * i] = v.x; a[2 * i + 1] = v.y; }
 #pragma unroll
                 for (int c = 0; c < 6; c++) {
                     double bcol[6];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) bcol[k] = ej[c * 6 + k];
+                    for (int k = 0; k < 3; k++) { const double2 v = ej[c * 3 + k]; bcol[2 * k] = v.x; bcol[2 * k + 1] = v.y; }
 #pragma unroll
                     for (int r = 0; r < 6; r++) {
                         double s = acc[r * 6 + c];
