@@ -180,7 +180,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     (void)attr_done;
     const long long N = p->dp.N;
-    const int grid1 = (int)std::max<long long>(1, std::min<long long>(2LL * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
+    const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
     const int per_sm2 = smem2 * ACC_CTAS_PER_SM <= p->smem_optin ? ACC_CTAS_PER_SM : std::max<int>(1, (int)(p->smem_optin / smem2));
     const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm2 * p->num_sms, (N + ACC_WARPS * 32 - 1) / (ACC_WARPS * 32)));
     prof_mark(p, 7);

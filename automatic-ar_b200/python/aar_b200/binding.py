@@ -14,7 +14,7 @@ import numpy as np
 
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # automatic-ar_b200/
 REPO_ROOT = os.path.dirname(PKG_ROOT)
-LIB_PATH = os.path.join(PKG_ROOT, "libaar_cuda.so")
+LIB_PATH = os.environ.get("AAR_LIB", os.path.join(PKG_ROOT, "libaar_cuda.so"))   # AAR_LIB: development aid (kernel variants)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
