@@ -524,6 +524,17 @@ int aar_shard_plan(const aar_problem_desc *d, int32_t *frame_begin, int32_t *fra
     return AAR_OK;
 }
 
+int aar_row_map(const aar_problem_desc *d, int64_t capacity, int32_t *of, int32_t *oc, int32_t *om, int32_t *oj, int64_t *num_observations) {
+    aar_problem *p = nullptr;
+    int rc = create_impl(d, &p, true);
+    if (rc) return rc;
+    if (num_observations) *num_observations = p->N;
+    if (p->N > capacity && (of || oc || om || oj)) { delete p; set_err("aar_row_map: capacity too small"); return AAR_ERR_INVALID; }
+    rc = aar_index_maps(p, of, oc, om, oj, nullptr, nullptr, nullptr, nullptr, nullptr);
+    delete p;
+    return rc;
+}
+
 void aar_problem_destroy(aar_problem *p) {
     if (!p) return;
     if (!p->stream && !p->h_st) { delete p; return; }   // host-only handle

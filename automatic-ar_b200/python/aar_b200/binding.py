@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 EXPORTS = ["aar_lm_default_params", "aar_problem_create", "aar_problem_destroy", "aar_last_error", "aar_num_vars",
            "aar_num_observations", "aar_num_local_observations", "aar_jacobian_nnz", "aar_index_maps", "aar_get_observations",
            "aar_mats2evec", "aar_evec2mats", "aar_eval_residual", "aar_eval_jacobian", "aar_reduced_system", "aar_lm_solve",
-           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_shard_plan", "aar_comm_unique_id", "aar_comm_init",
+           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_shard_plan", "aar_row_map", "aar_comm_unique_id", "aar_comm_init",
            "aar_kernel_launches", "aar_set_profiling", "aar_get_phase_ms"]
 
 
@@ -111,6 +111,16 @@ class Problem:
         fb = C.c_int32(0); fe = C.c_int32(0); ob = C.c_int64(0); oe = C.c_int64(0); n = C.c_int64(0)
         _chk(lib().aar_shard_plan(C.byref(d), C.byref(fb), C.byref(fe), C.byref(ob), C.byref(oe), C.byref(n)), "aar_shard_plan")
         return fb.value, fe.value, ob.value, oe.value, n.value
+
+    @staticmethod
+    def row_map(rig):
+        """aar_row_map: the bit-exact observation -> row map (frame / camera / marker indices, has_jacobian), host only."""
+        d, keep = Problem._desc(rig, True, True, True, True, False, 0, None, 0, 1, 0.0)
+        n = C.c_int64(0)
+        _chk(lib().aar_row_map(C.byref(d), C.c_int64(0), None, None, None, None, C.byref(n)), "aar_row_map")
+        of = np.zeros(n.value, np.int32); oc = np.zeros(n.value, np.int32); om = np.zeros(n.value, np.int32); oj = np.zeros(n.value, np.int32)
+        _chk(lib().aar_row_map(C.byref(d), n, _vp(of), _vp(oc), _vp(om), _vp(oj), C.byref(n)), "aar_row_map")
+        return dict(frame_idx=of, cam_idx=oc, marker_idx=om, has_jac=oj)
 
     @staticmethod
     def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta):

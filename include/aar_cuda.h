@@ -150,6 +150,12 @@ int aar_track_batch(aar_problem *p, double *z6_inout, const aar_lm_params *param
  * (row / 8) range.  Any output pointer may be NULL. */
 int aar_shard_plan(const aar_problem_desc *desc, int32_t *frame_begin, int32_t *frame_end, int64_t *obs_begin, int64_t *obs_end, int64_t *num_observations);
 
+/* The observation -> residual-row map of fill_iteration_arrays (multicam_mapper.cpp:345-377) computed on the host
+ * without touching a device: per kept observation, in row order (row0 = 8 * ordinal), the frame / camera / marker
+ * INDEX and whether it owns Jacobian rows.  Arrays may be NULL (count only); capacity = their length. */
+int aar_row_map(const aar_problem_desc *desc, int64_t capacity, int32_t *obs_frame_idx, int32_t *obs_cam_idx, int32_t *obs_marker_idx,
+                int32_t *obs_has_jacobian, int64_t *num_observations);
+
 /* multi-GPU: one handle per rank; id is the 128-byte ncclUniqueId created on rank 0 */
 int aar_comm_unique_id(void *id128);
 int aar_comm_init(aar_problem *p, const void *id128);

@@ -233,3 +233,49 @@ def test_track_batch_matches_reference_per_frame(binding, oracle_mod, with_huber
         tol = 1e-5 if with_huber else 1e-6
         assert abs(cost_g[k] - fc_o) <= tol * max(fc_o, 1e-12), (k, cost_g[k], fc_o)
         assert np.abs(z_g[k] - z_o).max() <= tol * max(1.0, np.abs(z_o).max()), k
+
+
+def test_edge_cases_ragged_inputs(binding, oracle_mod):
+    """Ragged / degenerate inputs the reference handles: one camera only (no camera block), one marker only (no marker
+    block), frames whose detections were all erased, duplicated detections, and an exact-staging re-run of the Jacobian."""
+    # one camera: n_r = 6 (M - 1); one marker: n_r = 6 (C - 1)
+    for kw in (dict(C=1, M=5), dict(C=3, M=1)):
+        rig = synth.make_rig(F=30, obs_per_frame=4.0 if kw["M"] > 1 else 2.5, seed=17, **kw)
+        o = oracle_mod.Oracle(rig); p = binding.Problem(rig)
+        z0 = o.mats2evec()
+        assert p.num_vars == o.num_vars
+        assert np.array_equal(p.residual(z0)[0], o.error(z0))
+        cp_o, ri_o, v_o = o.jacobian(z0); cp_g, ri_g, v_g = p.jacobian(z0)
+        assert np.array_equal(cp_o, cp_g) and np.array_equal(ri_o, ri_g) and np.array_equal(v_o, v_g)
+        for k in (1, 3):
+            o.set_max_iters(k)
+            z_o, fc_o, it_o, _ = o.solve(z0)
+            z_g, fc_g, it_g, _ = p.solve(z0, binding.Problem.default_params(max_iters=k))
+            assert it_o == it_g and abs(fc_g - fc_o) <= 1e-10 * fc_o and np.abs(z_g - z_o).max() <= 1e-9 * max(1.0, np.abs(z_o).max())
+    # a frame whose only detections belong to an unknown marker: it keeps its pose variables but contributes no rows
+    rig = small_rig(seed=19, F=12)
+    f_kill = rig.frame_ids[4]
+    sel = rig.det_frame == f_kill
+    rig.det_marker = rig.det_marker.copy(); rig.det_marker[sel] = 99999
+    o = oracle_mod.Oracle(rig); p = binding.Problem(rig)
+    z0 = o.mats2evec()
+    assert p.num_obs == o.num_rows // 8 == (~sel).sum()
+    assert np.array_equal(p.residual(z0)[0], o.error(z0))
+    S_o, b_o, c_o = o.reduced_system(z0, 10.0); S_g, b_g, c_g = p.reduced_system(z0, 10.0)
+    iu = np.triu_indices(p.n_r)
+    assert np.abs(S_g[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b_g - b_o).max() <= 1e-10 * np.abs(b_o).max()
+    z_g, fc_g, it_g, tr_g = p.solve(z0, binding.Problem.default_params(max_iters=2))
+    col = p.index_maps()["col_frame"][4]
+    assert np.array_equal(z_g[col:col + 6], z0[col:col + 6])        # (H + mu I) delta = 0 for a frame without rows: the pose stays put
+
+
+def test_exact_staging_fallback_matches(binding, oracle_mod, monkeypatch):
+    """The FP64-staging instantiation of the Jacobian kernels (taken when a central-difference numerator does not fit a
+    float) must give the same normal equations as the float32 staging."""
+    rig = small_rig(seed=23, F=30)
+    o = oracle_mod.Oracle(rig); z0 = o.mats2evec()
+    S32, b32, _ = binding.Problem(rig).reduced_system(z0, 77.0)
+    monkeypatch.setenv("AAR_FORCE_EXACT_STAGING", "1")
+    S64, b64, _ = binding.Problem(rig).reduced_system(z0, 77.0)
+    iu = np.triu_indices(len(b32))
+    assert np.abs(S32[iu] - S64[iu]).max() <= 1e-13 * np.abs(S64).max() and np.abs(b32 - b64).max() <= 1e-13 * np.abs(b64).max()
