@@ -103,6 +103,7 @@ struct aar_problem {
     // ---- staged central-difference numerators ([144][N] float32, or float64 in the exact fallback) and residuals ([8][N])
     DevBuf<float> d_Jn32; DevBuf<double> d_Jn64, d_Rv;
     int max_ms = 0, num_sms = 148; size_t smem_optin = 227 * 1024;
+    bool use_cluster_solve = true;
     int force_exact_staging = 0; long long exact_reruns = 0;
     DevProblem dp{};
     // ---- LM host mirror
@@ -259,11 +260,24 @@ int build_and_solve_reduced(aar_problem *p) {
     if (n_r > 0) {
         int rc = allreduce(p, S, (size_t)n_r * n_r + 2 * n_r, ncclSum);
         if (rc) return rc;
-        {   // cooperative launch: one CTA per block row of 32 (all co-resident: n_r / 32 <= number of SMs)
+        const int nblk = (n_r + CH_NB - 1) / CH_NB;
+        bool done = false;
+        if (nblk <= 16 && p->use_cluster_solve) {
+            // one thread-block cluster, the factor lives in distributed shared memory (aar_dense.cuh)
+            const size_t smem = ((size_t)CH_NB * (nblk * CH_NB + 2) + 3 * CH_NB * CH_LD + (size_t)nblk * CH_NB + CH_NB) * sizeof(double);
+            cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = p->stream;
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const double *Sc = S, *bc = b; const LmState *stp = p->d_st.p;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduced_solve_cluster, n_r, Sc, bc, p->d_dr.p, stp, p->d_flag.p);
+            if (e == cudaSuccess) { done = true; p->launches++; }
+            else { cudaGetLastError(); p->use_cluster_solve = false; }      // e.g. the cluster cannot be scheduled: fall back for good
+        }
+        if (!done) {   // cooperative launch: one CTA per block row of 32 (all co-resident: n_r / 32 <= number of SMs)
             int n = n_r; double *xs = p->d_dr.p; const LmState *stp = p->d_st.p; int *fl = p->d_flag.p; const double *bb = b;
             double *xinv = p->d_xinv.p;
             void *args[] = {&n, &S, &bb, &xs, &stp, &fl, &xinv};
-            const int gridc = std::max(1, std::min((n_r + CH_NB - 1) / CH_NB, p->num_sms));
+            const int gridc = std::max(1, std::min(nblk, p->num_sms));
             CU(cudaLaunchCooperativeKernel((const void *)k_reduced_solve, dim3(gridc), dim3(CH_THREADS), args, 0, p->stream));
             p->launches++;
         }
@@ -504,6 +518,14 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     }
     { const char *e = getenv("AAR_FORCE_EXACT_STAGING"); p->force_exact_staging = e && *e == '1'; }   // test hook: FP64 staging of the Jacobian block
     CU(cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    {   // cluster Cholesky: up to 16 CTAs per cluster (non-portable size), block row + staging in shared memory
+        const int nblk = (p->n_r + CH_NB - 1) / CH_NB;
+        const size_t smem = ((size_t)CH_NB * (nblk * CH_NB + 2) + 3 * CH_NB * CH_LD + (size_t)nblk * CH_NB + CH_NB) * sizeof(double);
+        const char *e = getenv("AAR_NO_CLUSTER_SOLVE");
+        if (nblk > 16 || smem > p->smem_optin - 1024 || (e && *e == '1')) p->use_cluster_solve = false;
+        else if (cudaFuncSetAttribute(k_reduced_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                 cudaFuncSetAttribute(k_reduced_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); p->use_cluster_solve = false; }
+    }
     if ((size_t)p->n_r * sizeof(double) > 48 * 1024) CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)p->n_r * sizeof(double))));
     CU(cudaStreamSynchronize(p->stream));
     aar_lm_default_params(&p->params);

@@ -172,4 +172,156 @@ __global__ void __launch_bounds__(CH_THREADS) k_reduced_solve(int n, double *__r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cluster variant for n <= 512 (every BASELINE configuration: n_r = 468 at cfg 4): ONE thread-block cluster of
+// nblk <= 16 CTAs, CTA i owns block row i of the matrix in its shared memory for the whole solve, tiles of other
+// block rows are read through distributed shared memory and the 2 synchronisations per block column are hardware
+// cluster barriers instead of grid-wide barriers through global memory.  Nothing but the initial load and the
+// final x touches global memory.  Same left-looking algorithm and same inverse-diagonal-block trick as above.
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ void tile_product_2x2(const double *A, int lda, const double *B, int ldb, int ty, int tx, double &c00, double &c01, double &c10, double &c11) {
+#pragma unroll 8
+    for (int q = 0; q < CH_NB; q++) {
+        const double a0 = A[ty * lda + q], a1 = A[(ty + 16) * lda + q], b0 = B[tx * ldb + q], b1 = B[(tx + 16) * ldb + q];
+        c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS) k_reduced_solve_cluster(int n, const double *__restrict__ S, const double *__restrict__ b, double *__restrict__ x, const LmState *__restrict__ st,
+                                                                      int *__restrict__ chol_fail) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double sm[];
+    const int nblk = (n + CH_NB - 1) / CH_NB, LD = nblk * CH_NB + 2;
+    double *sRow = sm;                                   // [32][LD]   block row `me` of the matrix / of L
+    double *sT = sRow + CH_NB * LD;                      // [32][33]   staging of a remote tile
+    double *sX = sT + CH_NB * CH_LD;                     // [32][33]   inverse of this CTA's diagonal factor
+    double *sXr = sX + CH_NB * CH_LD;                    // [32][33]   staging of a remote inverse
+    double *sy = sXr + CH_NB * CH_LD;                    // [nblk*32]  right-hand side / y / x, replicated in every CTA
+    double *ss = sy + nblk * CH_NB;                      // [32]       partial sums of the back substitution
+    __shared__ double sv[CH_NB + 1];
+    const int me = (int)cluster.block_rank(), tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const double mu = st->mu;
+    // ---- load block row `me` (lower part from the UPPER triangle of S), mu on the diagonal, identity padding
+    for (int e = tid; e < CH_NB * nblk * CH_NB; e += CH_THREADS) {
+        const int r = e / (nblk * CH_NB), c = e % (nblk * CH_NB), gr = me * CH_NB + r;
+        double v = 0.0;
+        if (gr < n && c <= gr) v = S[(size_t)c * n + gr] + (c == gr ? mu : 0.0);
+        else if (gr >= n && c == gr) v = 1.0;
+        sRow[r * LD + c] = v;
+    }
+    for (int e = tid; e < nblk * CH_NB; e += CH_THREADS) sy[e] = e < n ? b[e] : 0.0;
+    if (tid < CH_NB) ss[tid] = 0.0;
+    cluster.sync();
+    for (int k = 0; k <= me; k++) {
+        // ---- own tile (me, k) -= sum_{j<k} L(me, j) L(k, j)^T ; L(k, j) from CTA k through distributed shared memory
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        const double *rowk = cluster.map_shared_rank(sRow, k);
+        for (int j = 0; j < k; j++) {
+            const double *B;
+            int ldb;
+            if (k == me) { B = sRow + j * CH_NB; ldb = LD; }
+            else {
+                __syncthreads();
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sT[(e / CH_NB) * CH_LD + e % CH_NB] = rowk[(e / CH_NB) * LD + j * CH_NB + e % CH_NB];
+                __syncthreads();
+                B = sT; ldb = CH_LD;
+            }
+            tile_product_2x2(sRow + j * CH_NB, LD, B, ldb, ty, tx, c00, c01, c10, c11);
+        }
+        __syncthreads();
+        double *C = sRow + k * CH_NB;
+        C[ty * LD + tx] -= c00; C[ty * LD + tx + 16] -= c01; C[(ty + 16) * LD + tx] -= c10; C[(ty + 16) * LD + tx + 16] -= c11;
+        __syncthreads();
+        if (k == me) {
+            // ---- diagonal block: L_kk = chol(C) in place, then X = L_kk^-1
+            for (int j = 0; j < CH_NB; j++) {
+                if (tid == 0) { double d = C[j * LD + j]; if (!(d > 0)) { atomicExch(chol_fail, 1); d = 1; } sv[0] = sqrt(d); }
+                __syncthreads();
+                const double dj = sv[0];
+                if (tid > j && tid < CH_NB) C[tid * LD + j] /= dj;
+                if (tid == j) C[j * LD + j] = dj;
+                __syncthreads();
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                    const int r = e / CH_NB, c = e % CH_NB;
+                    if (c > j && r >= c) C[r * LD + c] = fma(-C[r * LD + j], C[c * LD + j], C[r * LD + c]);
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {      // lane c: column c of X by forward substitution, X column kept in registers
+                double xc[CH_NB];
+#pragma unroll
+                for (int r = 0; r < CH_NB; r++) {
+                    double v = r == lane ? 1.0 : 0.0;
+#pragma unroll
+                    for (int q = 0; q < CH_NB; q++) if (q < r) v = fma(-C[r * LD + q], xc[q], v);
+                    xc[r] = r < lane ? 0.0 : v / C[r * LD + r];
+                }
+#pragma unroll
+                for (int r = 0; r < CH_NB; r++) sX[r * CH_LD + lane] = xc[r];
+            }
+            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) { const int r = e / CH_NB, c = e % CH_NB; if (c > r) C[r * LD + c] = 0.0; }
+        }
+        cluster.sync();                                  // L_kk and X_k are visible to the cluster
+        if (k < me) {
+            // ---- L(me, k) = C X_k^T
+            const double *Xk = cluster.map_shared_rank(sX, k);
+            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sXr[(e / CH_NB) * CH_LD + e % CH_NB] = Xk[(e / CH_NB) * CH_LD + e % CH_NB];
+            __syncthreads();
+            double d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+            tile_product_2x2(C, LD, sXr, CH_LD, ty, tx, d00, d01, d10, d11);
+            __syncthreads();
+            C[ty * LD + tx] = d00; C[ty * LD + tx + 16] = d01; C[(ty + 16) * LD + tx] = d10; C[(ty + 16) * LD + tx + 16] = d11;
+        }
+        cluster.sync();                                  // block column k of L is final
+    }
+    // CTAs with me < k idle through the remaining steps but must take part in the barriers
+    for (int k = me + 1; k < nblk; k++) { cluster.sync(); cluster.sync(); }
+    // ---- forward substitution  L y = b : CTA k owns block row k, y_k is broadcast into every CTA's sy
+    for (int k = 0; k < nblk; k++) {
+        if (k == me) {
+            // t = b_k - sum_{c < 32k} L(k, c) y_c   (rows by warps, dot products by lanes)
+            for (int r = warp; r < CH_NB; r += CH_THREADS / 32) {
+                double s = 0;
+                for (int c = lane; c < k * CH_NB; c += 32) s = fma(sRow[r * LD + c], sy[c], s);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) sv[r] = sy[k * CH_NB + r] - s;
+            }
+            __syncthreads();
+            if (tid < CH_NB) {    // y_k = X_k t
+                double s = 0;
+                for (int q = 0; q <= tid; q++) s = fma(sX[tid * CH_LD + q], sv[q], s);
+                for (int rk = 0; rk < nblk; rk++) cluster.map_shared_rank(sy, rk)[k * CH_NB + tid] = s;
+            }
+        }
+        cluster.sync();
+    }
+    // ---- back substitution  L^T x = y : x_i = X_i^T (y_i - s_i), then every CTA k < i adds L(i, k)^T x_i to its s_k
+    for (int i = nblk - 1; i >= 0; i--) {
+        if (i == me) {
+            if (tid < CH_NB) sv[tid] = sy[i * CH_NB + tid] - ss[tid];
+            __syncthreads();
+            if (tid < CH_NB) {
+                double s = 0;
+                for (int q = tid; q < CH_NB; q++) s = fma(sX[q * CH_LD + tid], sv[q], s);
+                for (int rk = 0; rk < nblk; rk++) cluster.map_shared_rank(sy, rk)[i * CH_NB + tid] = s;      // x_i overwrites y_i
+                if (i * CH_NB + tid < n) x[i * CH_NB + tid] = s;
+            }
+        }
+        cluster.sync();
+        if (me < i) {
+            const double *rowi = cluster.map_shared_rank(sRow, i);       // tile (i, me) lives in CTA i
+            if (tid < CH_NB) {
+                double s = 0;
+                for (int q = 0; q < CH_NB; q++) s = fma(rowi[q * LD + me * CH_NB + tid], sy[i * CH_NB + q], s);
+                ss[tid] += s;
+            }
+        }
+        __syncthreads();
+    }
+    cluster.sync();                                      // no CTA may exit while its shared memory can still be read remotely
+}
+
 } // namespace aar
