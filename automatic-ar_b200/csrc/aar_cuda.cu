@@ -168,7 +168,6 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     const size_t smem1 = tabs_smem ? tab_bytes : 0;
     static thread_local const void *attr_done[4] = {nullptr, nullptr, nullptr, nullptr};
     auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT>;
-    const size_t hcm_d = (size_t)p->nrc * p->nrm * 36;
     const size_t scr = (size_t)ACC_WARPS * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
     // as many camera x marker pair accumulators as the shared memory left over by the fixed part can hold
     AccPlan pl; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
@@ -245,7 +244,7 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
         LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
         // two CTAs per SM, at most two full waves (no tail wave), at least a few pipeline stages per CTA
-        const int nchunks = std::max(1, std::min((4 * p->num_sms) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
+        const int nchunks = std::max(1, std::min((2 * AAR_SY_MINBLOCKS * p->num_sms) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
         LAUNCH(p, k_schur_syrk, ntiles * nchunks, SY_THREADS, SY_SMEM, p->dp, nb, tiles_side, nchunks, p->d_frame_block_slot.p, p->d_E.p, S);
     }
     return AAR_OK;
@@ -254,7 +253,7 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
 // one try of the do-while of SparseLevMarq::step (sparselevmarq.h:384-419) up to (not including) the decision
 int build_and_solve_reduced(aar_problem *p) {
     const int n_r = p->n_r;
-    double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
+    double *S = p->d_red.p, *b = S + (size_t)n_r * n_r;     // [S | b | Br]: Br = -gr is kept for the gain denominator
     if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, S);
     { int rc = schur_eliminate(p, S, b); if (rc) return rc; }
     if (n_r > 0) {
@@ -283,7 +282,6 @@ int build_and_solve_reduced(aar_problem *p) {
         }
         LAUNCH(p, k_apply_reduced, cdiv(n_r, 128), 128, 0, n_r, p->d_z.p, p->d_dr.p, p->d_zt.p);
     }
-    (void)Br;
     return AAR_OK;
 }
 

@@ -82,7 +82,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
-__global__ void __launch_bounds__(SY_THREADS, 2) k_schur_syrk(DevProblem p, int nb, int tiles_side, int nchunks, const int *__restrict__ frame_block_slot,
+#ifndef AAR_SY_MINBLOCKS
+#define AAR_SY_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(SY_THREADS, AAR_SY_MINBLOCKS) k_schur_syrk(DevProblem p, int nb, int tiles_side, int nchunks, const int *__restrict__ frame_block_slot,
                                                               const double *__restrict__ E, double *__restrict__ S) {
     extern __shared__ __align__(16) unsigned char sy_raw[];
     typedef double EBuf[2][SY_FB][SY_TB * SY_LD];          // [I|J][frame in batch][block][36 (+1)]
