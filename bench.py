@@ -147,6 +147,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version banner to STDOUT when this is set: stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     binding.lib()
     t0 = time.time()
