@@ -166,7 +166,6 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     const size_t tab_bytes = ((size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB) * sizeof(double);
     const int tabs_smem = tab_bytes <= 96 * 1024;
     const size_t smem1 = tabs_smem ? tab_bytes : 0;
-    static thread_local const void *attr_done[4] = {nullptr, nullptr, nullptr, nullptr};
     auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT>;
     const size_t scr = (size_t)ACC_WARPS * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
     // as many camera x marker pair accumulators as the shared memory left over by the fixed part can hold
@@ -178,7 +177,6 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     if (smem2 > p->smem_optin - 1024) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    (void)attr_done;
     const long long N = p->dp.N;
     const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
     const int per_sm2 = smem2 * ACC_CTAS_PER_SM <= p->smem_optin ? ACC_CTAS_PER_SM : std::max<int>(1, (int)(p->smem_optin / smem2));
