@@ -137,6 +137,36 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def track_line(device, with_cpu):
+    """BASELINE config 5 (track mode) on a bounded sample: batched per-frame 6-dof LM against the fixed rig, host z in/out."""
+    import copy
+    import numpy as np
+    from aar_b200 import binding, synth
+    frames = 5000
+    rig = copy.copy(synth.make_config("cfg5", frames=frames))
+    rig.T_cam_init, rig.T_marker_init = rig.T_cam_true, rig.T_marker_true        # the solved rig is fixed while tracking
+    p = binding.Problem(rig, cams=False, markers=False, objects=True, device=device)
+    z0 = p.mats2evec().reshape(-1, 6)
+    p.track_batch(z0)
+    t = time.time(); z, cost, its = p.track_batch(z0); dt = time.time() - t
+    out = {"workload": "cfg5 sample: %d independent frames, %d marker observations" % (rig.F, p.num_obs), "frames_per_s": rig.F / dt,
+           "ms": 1e3 * dt, "lm_iterations_mean": float(its.mean()), "rms_px": float(np.sqrt(cost.sum() / (8 * p.num_obs))),
+           "timing": "host wall clock around aar_track_batch (host z in / out, copies included)"}
+    p.close()
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py
+        o = oracle_py.Oracle(rig); o.set_config(cams=False, markers=False, objects=True)
+        n = 8; t = time.time()
+        for k in range(n):
+            sel = rig.det_frame == rig.frame_ids[k]
+            rows, zi = o.track_init(int(rig.frame_ids[k]), rig.T_frame_init[k], rig.det_cam[sel], rig.det_marker[sel], rig.det_xy[sel])
+            (o.track_ref if o.is_ref else o.track_port)(zi)
+        out["cpu_frames_per_s"] = n / (time.time() - t); out["cpu_sample_frames"] = n
+        out["cpu_kind"] = "reference" if o.is_ref else "port"
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -280,6 +310,11 @@ def run_ours(args, rank, world, local_rank):
             "phases_ms_per_step": {k: v / K for k, v in ph.items() if k != "jacobian_launches"}, "total_tries": int(tries_total),
             "setup_s": {"generate": t_gen, "create_upload_undistort": t_create},
         }
+        if world == 1 and not args.no_track:
+            try:
+                line["track"] = track_line(local_rank, not args.no_cpu_baseline)
+            except Exception as e:      # the headline measurement above stands on its own
+                line["track"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(args.workload, CPU_SAMPLE_FRAMES, CPU_SAMPLE_ITERS)
             line["cpu_baseline"] = {"value": 4.0 * r["n_obs"] * r["iters"] / r["seconds"], "unit": "corner-observations/s", "cores": r["cores"],
@@ -300,6 +335,7 @@ def main():
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-track", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
