@@ -104,6 +104,7 @@ struct aar_problem {
     DevBuf<float> d_Jn32; DevBuf<double> d_Jn64, d_Rv;
     int max_ms = 0, num_sms = 148; size_t smem_optin = 227 * 1024;
     bool use_cluster_solve = true;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_slab[16] = {}; cudaEvent_t ev_join = nullptr; int jac_slabs = 1;
     int force_exact_staging = 0; long long exact_reruns = 0;
     DevProblem dp{};
     // ---- LM host mirror
@@ -160,35 +161,59 @@ int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_ou
 
 void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
 
-// launches one of the two Jacobian kernels with the shared-memory carve-up it needs
-template <typename JT>
-int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
+// Launches the two Jacobian kernels.  With more than one slab the observations are cut into slabs and the two
+// kernels run on two streams, k_jac_accumulate of slab s next to k_jac_project of slab s+1 on the same SMs (one
+// 192-thread x 168-register CTA of the first and one 128-thread x 255-register CTA of the second fill the register file
+// of an SM together): the first is bound by FP64 issue, the second by the latency of its reduce / emit sequences, so
+// each could fill the other's bubbles.  MEASURED SLOWER on cfg 4 (profiles/r1_notes.md: 9.2 ms vs 6.35 ms per 5.1 M observations,
+// the projection kernel needs its 12 warps/SM), so the default is one slab; AAR_JAC_SLABS=n keeps the experiment reachable.
+template <typename JT, int AW>
+int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
     const size_t tab_bytes = ((size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB) * sizeof(double);
     const int tabs_smem = tab_bytes <= 96 * 1024;
     const size_t smem1 = tabs_smem ? tab_bytes : 0;
-    auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT>;
-    const size_t scr = (size_t)ACC_WARPS * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
-    // as many camera x marker pair accumulators as the shared memory left over by the fixed part can hold
+    auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT, AW>;
+    const size_t scr = (size_t)AW * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
+    // as many camera x marker pair accumulators as the shared memory left over by the fixed part (and, when the two
+    // kernels share an SM, by the projection kernel's tables) can hold
     AccPlan pl; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
     { const char *e = getenv("AAR_ACC_SKIP"); pl.skip = e ? atoi(e) : 0; }
-    const size_t room = p->smem_optin - 2048 > fix + scr ? p->smem_optin - 2048 - fix - scr : 0;
-    pl.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, room / 288);
+    const size_t avail = p->smem_optin - 2048 - (slabs > 1 ? smem1 + 2048 : 0);
+    if (fix + scr > avail) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
+    pl.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, (avail - fix - scr) / 288);
     const size_t smem2 = fix + (size_t)pl.hcm_smem * 288 + scr;
-    if (smem2 > p->smem_optin - 1024) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const long long N = p->dp.N;
-    const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
-    const int per_sm2 = smem2 * ACC_CTAS_PER_SM <= p->smem_optin ? ACC_CTAS_PER_SM : std::max<int>(1, (int)(p->smem_optin / smem2));
-    const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm2 * p->num_sms, (N + ACC_WARPS * 32 - 1) / (ACC_WARPS * 32)));
+    const long long per = slabs > 1 ? ((N + slabs - 1) / slabs + 31) / 32 * 32 : N;
+    cudaStream_t s2 = slabs > 1 ? p->stream2 : p->stream;
     prof_mark(p, 7);
-    k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p);
-    p->launches++;
-    prof_mark(p, 9);
-    k2<<<grid2, ACC_WARPS * 32, smem2, p->stream>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
-    p->launches++;
+    int done = 0;
+    for (long long a = 0; a < N; a += per, done++) {
+        const long long b = std::min(N, a + per), n = b - a;
+        const int per_sm1 = slabs > 1 ? 1 : AAR_PROJ_MINBLOCKS;
+        const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm1 * p->num_sms, (n + PROJ_THREADS - 1) / PROJ_THREADS));
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)p->num_sms, (n + AW * 32 - 1) / (AW * 32)));
+        k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, a, b);
+        p->launches++;
+        if (slabs > 1) { CU(cudaEventRecord(p->ev_slab[done & 15], p->stream)); CU(cudaStreamWaitEvent(s2, p->ev_slab[done & 15], 0)); }
+        else prof_mark(p, 9);
+        k2<<<grid2, AW * 32, smem2, s2>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, a, b);
+        p->launches++;
+    }
+    if (slabs > 1) {
+        prof_mark(p, 9);                                   // end of the projection kernels on the main stream
+        CU(cudaEventRecord(p->ev_join, s2)); CU(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+    }
     prof_mark(p, 8);
     return AAR_OK;
+}
+template <typename JT>
+int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
+    int slabs = p->jac_slabs;
+    if (p->dp.N < 64LL * 1024 * slabs) slabs = 1;          // small problems: one launch each, nothing to overlap
+    if (slabs > 16) slabs = 16;
+    return slabs > 1 ? launch_jacobian_t<JT, 4>(p, huber_eval, Jn, slabs) : launch_jacobian_t<JT, 8>(p, huber_eval, Jn, 1);
 }
 
 // J^T J blocks and J^T r at d_z (sparselevmarq.h:353-367) into Hf / W / Hrr / gr; or the dense per-observation
@@ -429,6 +454,10 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     CU(cudaSetDevice(p->device));
     if (d->stream) p->stream = (cudaStream_t)d->stream; else { CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
     for (auto &e : p->ev) CU(cudaEventCreate(&e));
+    CU(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    for (auto &e : p->ev_slab) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    { const char *e = getenv("AAR_JAC_SLABS"); if (e && atoi(e) >= 1) p->jac_slabs = atoi(e); }
     CU(cudaMallocHost((void **)&p->h_st, sizeof(LmState)));
     CU(cudaMallocHost((void **)&p->h_red3, 8 * sizeof(double)));
     CU(cudaMallocHost((void **)&p->h_flags, 4 * sizeof(int)));
@@ -560,6 +589,9 @@ void aar_problem_destroy(aar_problem *p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : p->ev_slab) if (e) cudaEventDestroy(e);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->stream2) { cudaStreamSynchronize(p->stream2); cudaStreamDestroy(p->stream2); }
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_red3) cudaFreeHost(p->h_red3);
     if (p->h_flags) cudaFreeHost(p->h_flags);
