@@ -95,11 +95,6 @@ __global__ void k_expand_trial(DevProblem p, const double *__restrict__ z) {
     store_pose(p.fr_tr + (size_t)t * POSE_STRIDE, T);
 }
 
-struct ObsCtx {
-    int f, c, m; bool cam_root, mk_root, nojac;
-    Intr k;
-};
-
 // T1 = inv(Tc) * To (skipped for the root camera, mcm.cpp:617-621)
 __device__ __forceinline__ void make_T1(bool cam_root, const Pose &ci, const Pose &To, Pose &T1) {
     if (cam_root) { T1 = To; return; }
