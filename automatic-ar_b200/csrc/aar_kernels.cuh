@@ -120,6 +120,12 @@ __device__ __forceinline__ void load8(const float4 *a, const float4 *b, long lon
     x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
 }
 
+} // namespace aar
+
+#include "aar_jacobian.cuh"
+
+namespace aar {
+
 // eval_curr_solution (mcm.cpp:996-1028): residuals of every observation + sum of squares.
 // cam/mk/fr: base pose tables with the given strides (trial tables or variant-0 of the Jacobian tables).
 __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam_stride, const double *__restrict__ mk, int mk_stride,
@@ -136,7 +142,12 @@ __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam
         if (!mk_root) load_pose(Tm, mk + (size_t)m * mk_stride);
         make_T1(cam_root, ci, To, T1);
         float pr[8], und[8];
-        project_T1_Tm(T1, mk_root, Tm, k, p.h, pr);
+        {   // same expressions as project() of aar_device_math.cuh, with the quotients of a corner sharing one reciprocal
+            double c0[3], c1[3], t[3];
+            if (mk_root) { c0[0] = T1.r[0]; c0[1] = T1.r[3]; c0[2] = T1.r[6]; c1[0] = T1.r[1]; c1[1] = T1.r[4]; c1[2] = T1.r[7]; t[0] = T1.t[0]; t[1] = T1.t[1]; t[2] = T1.t[2]; }
+            else { compose_R01(T1.r, Tm.r, c0, c1); compose_t(T1.r, T1.t, Tm.t, t); }
+            Offs of; make_offsets(c0, c1, k, p.h, of); project_offs(of, t, k, pr);
+        }
         load8(p.und_a, p.und_b, o, und);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -161,11 +172,6 @@ __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam
     }
 }
 
-} // namespace aar
-
-#include "aar_jacobian.cuh"
-
-namespace aar {
 
 // ---------------------------------------------------------------------------------------------
 // LM state, device resident (sparselevmarq.h:130-135, 237-249).
