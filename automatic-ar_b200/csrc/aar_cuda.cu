@@ -260,9 +260,9 @@ __global__ void k_prepare_reduced(int n_r, const double *__restrict__ Hrr, const
 // Schur elimination of the frame blocks of this rank into S (must hold Hrr) and b (must hold -gr)
 int schur_eliminate(aar_problem *p, double *S, double *b) {
     const int n_r = p->n_r, nb = p->nrc + p->nrm, F = p->dp.F;
-    if (!p->opt_f || F <= 0 || n_r <= 0) return AAR_OK;
-    LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);
-    if (p->nslots > 0) {
+    if (!p->opt_f || F <= 0) return AAR_OK;
+    LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);      // also feeds k_backsub
+    if (n_r > 0 && p->nslots > 0) {
         const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots * 6 + 255) / 256));
         LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
@@ -832,7 +832,8 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             prof_mark(p, 2);
             if ((rc = build_and_solve_reduced(p))) return rc;
             prof_mark(p, 3);
-            if (p->opt_f && p->dp.F > 0) LAUNCH(p, k_backsub, cdiv(p->dp.F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_W.p, p->d_dr.p, p->d_z.p, p->d_zt.p, p->d_red3.p);
+            if (p->opt_f && p->dp.F > 0)
+                LAUNCH(p, k_backsub, std::max(1, std::min(4 * p->num_sms, (int)cdiv(p->dp.F, BS_WARPS))), BS_WARPS * 32, 0, p->dp, p->d_fc.p, p->d_Hf.p, p->d_W.p, p->d_dr.p, p->d_z.p, p->d_zt.p, p->d_red3.p);
             prof_mark(p, 4);
             residual(p, p->d_zt.p, p->huber_cur, nullptr);
             prof_mark(p, 5);

@@ -10,6 +10,7 @@ namespace aar {
 constexpr int NVAR_CAM = 13;   // inverse camera transform: base + 6 dof x (+,-)
 constexpr int NVAR_RT = 7;     // marker / frame: base + 3 rotation dof x (+,-); translations are perturbed on the fly
 constexpr int POSE_STRIDE = 12;
+constexpr int FC_STRIDE_K = 28;  // per frame: packed lower Cholesky factor of Hff + mu I (21) | y = L^-1 Bf (6) | pad  (aar_schur.cuh: FC_STRIDE)
 
 // Everything the kernels need, by value.
 struct DevProblem {
@@ -233,34 +234,69 @@ __device__ __forceinline__ void bwd6(const double *L, double *x) {
     }
 }
 
-// Back-substitution delta_f = D^-1 (Bf - W_f^T delta_r) (one thread per frame), trial point z + delta,
-// and the frame part of the two dot products needed by L = 1/2 delta^T (mu delta - B) (sparselevmarq.h:406).
-__global__ void k_backsub(DevProblem p, const LmState *__restrict__ st, const double *__restrict__ Hf, const double *__restrict__ W, const double *__restrict__ dr,
-                          const double *__restrict__ z, double *__restrict__ zt, double *__restrict__ red3) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
+// Back-substitution delta_f = D^-1 (Bf - W_f^T delta_r), trial point z + delta, and the frame part of the two dot products
+// needed by L = 1/2 delta^T (mu delta - B) (sparselevmarq.h:406).  One warp per frame (persistent grid): lanes stride over
+// the frame's W slots (consecutive 288-byte blocks -> coalesced), the 6 partial sums meet by shuffles, lane 0 finishes with
+// the factor L and y = L^-1 B that k_frame_chol left in `fc`:  delta_f = L^-T (y - L^-1 sum_s W_s^T delta_r[s]).
+constexpr int BS_WARPS = 8;
+__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevProblem p, const double *__restrict__ fc, const double *__restrict__ Hf, const double *__restrict__ W,
+                                                           const double *__restrict__ dr, const double *__restrict__ z, double *__restrict__ zt, double *__restrict__ red3) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double dd = 0, dB = 0;
-    if (f < p.F) {
-        double L[36], rhs[6], B[6];
-        chol6(Hf + (size_t)f * HF_STRIDE, st->mu, L);
-#pragma unroll
-        for (int i = 0; i < 6; i++) { B[i] = -Hf[(size_t)f * HF_STRIDE + 21 + i]; rhs[i] = B[i]; }
+    for (int f = blockIdx.x * BS_WARPS + warp; f < p.F; f += gridDim.x * BS_WARPS) {
+        double acc[6] = {0, 0, 0, 0, 0, 0};
         const int s0 = p.frame_slot_ptr[f], s1 = p.frame_slot_ptr[f + 1];
-        for (int s = s0; s < s1; s++) {
+        for (int s = s0 + lane; s < s1; s += 32) {
             const double *w = W + (size_t)s * 36;
             const double *d = dr + 6 * p.slot_block[s];
 #pragma unroll
-            for (int i = 0; i < 6; i++)
+            for (int i = 0; i < 6; i++) {
+                const double di = d[i];
 #pragma unroll
-                for (int k = 0; k < 6; k++) rhs[k] = fma(-w[i * 6 + k], d[i], rhs[k]);
+                for (int k = 0; k < 6; k++) acc[k] = fma(w[i * 6 + k], di, acc[k]);
+            }
         }
-        fwd6(L, rhs); bwd6(L, rhs);
-        const size_t col = (size_t)p.col_frame0 + 6 * (size_t)f;
 #pragma unroll
-        for (int i = 0; i < 6; i++) { zt[col + i] = z[col + i] + rhs[i]; dd = fma(rhs[i], rhs[i], dd); dB = fma(rhs[i], B[i], dB); }
+        for (int k = 0; k < 6; k++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) {
+            const double *l = fc + (size_t)f * FC_STRIDE_K;
+            double v[6];
+            int idx = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {               // v = y - L^-1 acc  (forward substitution on acc, packed lower factor)
+                double t = acc[r];
+#pragma unroll
+                for (int k = 0; k < r; k++) t = fma(-l[idx + k], acc[k], t);
+                acc[r] = t / l[idx + r];
+                idx += r + 1;
+                v[r] = l[21 + r] - acc[r];
+            }
+#pragma unroll
+            for (int r = 5; r >= 0; r--) {              // delta = L^-T v
+                double t = v[r];
+#pragma unroll
+                for (int k = r + 1; k < 6; k++) t = fma(-l[k * (k + 1) / 2 + r], v[k], t);
+                v[r] = t / l[r * (r + 1) / 2 + r];
+            }
+            const size_t col = (size_t)p.col_frame0 + 6 * (size_t)f;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const double B = -Hf[(size_t)f * HF_STRIDE + 21 + i];
+                zt[col + i] = z[col + i] + v[i]; dd = fma(v[i], v[i], dd); dB = fma(v[i], B, dB);
+            }
+        }
     }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) { dd += __shfl_xor_sync(0xffffffffu, dd, s); dB += __shfl_xor_sync(0xffffffffu, dB, s); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(red3 + 1, dd); atomicAdd(red3 + 2, dB); }
+    // one pair of atomics per CTA
+    __shared__ double sdd[BS_WARPS], sdB[BS_WARPS];
+    if (lane == 0) { sdd[warp] = dd; sdB[warp] = dB; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < BS_WARPS; w++) { a += sdd[w]; b += sdB[w]; }
+        atomicAdd(red3 + 1, a); atomicAdd(red3 + 2, b);
+    }
 }
 
 // z_trial (reduced part) = z + delta_r

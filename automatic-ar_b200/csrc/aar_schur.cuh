@@ -14,7 +14,7 @@
 
 namespace aar {
 
-constexpr int FC_STRIDE = 28;      // per frame: L (lower, packed by rows, 21) | y (6) | pad
+constexpr int FC_STRIDE = FC_STRIDE_K;   // per frame: L (lower, packed by rows, 21) | y (6) | pad
 constexpr int SY_TB = 16;          // 6x6 blocks per tile side
 constexpr int SY_LD = 38;          // padded block stride in shared memory: 16-byte aligned blocks, conflict-free 128-bit loads across blocks
 constexpr int SY_FB = 4;           // frames per pipeline stage

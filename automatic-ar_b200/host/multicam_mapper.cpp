@@ -125,16 +125,24 @@ void MultiCamMapper::init(size_t root_c, const std::map<int, Mat44> &Tc, size_t 
         cam_configs[p.first] = cc[(size_t)p.first];
     }
     corners_undistorted = false;
+    // the handle of init() only runs remove_distortions; the reference's default Config has optimize_cam_intrinsics = true
+    // (find_solution switches it off before solve()), which the device path refuses — solve() reports that, not init()
+    Config keep = config; config.optimize_cam_intrinsics = false;
     make_handle(false);
     pull_undistorted();                                          // remove_distortions (:554-578) ran on the device
+    config = keep;
+    if (config.optimize_cam_intrinsics) drop_handle();
 }
 
 void MultiCamMapper::init(const std::map<int, Mat44> &object_poses, const FrameCamMarkers &fcm) {
     drop_handle();
     object_to_global = object_poses; frame_cam_markers = fcm;
     corners_undistorted = false;
+    Config keep = config; config.optimize_cam_intrinsics = false;
     make_handle(false);
     pull_undistorted();
+    config = keep;
+    if (config.optimize_cam_intrinsics) drop_handle();
 }
 
 void MultiCamMapper::make_handle(bool undist) {

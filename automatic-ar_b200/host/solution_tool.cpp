@@ -1,6 +1,9 @@
 // solution_tool — format round trips for the tests (no GPU needed):
 //   solution_tool roundtrip <in.solution> <out.solution> [<out.yaml>]     read + write back (must be byte identical)
 //   solution_tool detections <in.detections> <out.detections>             read + write back
+//   solution_tool resolve <in.solution> <out.solution>                    (GPU) re-create the mapper through the 8-argument
+//                         init() — the Initializer-output path: raw corners, device undistortion — and solve()
+#include <algorithm>
 #include <iostream>
 #include "multicam_mapper.h"
 int main(int argc, char **argv) {
@@ -16,6 +19,18 @@ int main(int argc, char **argv) {
             auto d = aar::MultiCamMapper::read_detections_file(argv[2]);
             aar::MultiCamMapper::write_detections_file(argv[3], d);
             std::cout << d.size() << " frames" << std::endl;
+        } else if (mode == "resolve") {
+            aar::MultiCamMapper in;
+            if (!in.read_solution_file(argv[2])) return 1;
+            int max_id = -1; for (auto &c : in.cam_configs) max_id = std::max(max_id, c.first);
+            std::vector<aar::CamConfig> confs((size_t)max_id + 1);
+            for (auto &c : in.cam_configs) confs[(size_t)c.first] = c.second;
+            aar::MultiCamMapper mcm(in.get_root_cam(), in.transforms_to_root_cam, in.get_root_marker(), in.transforms_to_root_marker, in.object_to_global,
+                                    in.frame_cam_markers, (float)in.get_marker_size(), confs);
+            mcm.set_optmize_flag_cam_intrinsics(false);
+            mcm.solve();
+            std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
+            if (!mcm.write_solution_file(argv[3])) return 1;
         } else return -1;
     } catch (const std::exception &e) { std::cerr << e.what() << std::endl; return 2; }
     return 0;

@@ -90,6 +90,22 @@ def test_find_solution_app_matches_binding(host_bins, tmp_path):
 
 
 @pytest.mark.gpu
+def test_eight_argument_init_path_matches_solution_file_path(host_bins, tmp_path):
+    """MultiCamMapper(root_c, T_to_root_cam, ..., fcm, m_size, cam_confs) — the Initializer-output constructor: raw corners are
+    undistorted on the device and pulled back into frame_cam_markers — must solve like the handle built from the file."""
+    rig = synth.make_config("cfg1")
+    a = str(tmp_path / "initial.solution")
+    synth.write_solution_file(a, rig)
+    out1 = subprocess.run([os.path.join(host_bins, "find_solution"), str(tmp_path), "0.05"], check=True, capture_output=True, text=True).stdout
+    out2 = subprocess.run([os.path.join(host_bins, "solution_tool"), "resolve", a, str(tmp_path / "resolved.solution")], check=True, capture_output=True, text=True).stdout
+    c1 = float(out1.split("final_error:")[1].split()[0]); c2 = float(out2.split("final_error:")[1].split()[0])
+    assert abs(c1 - c2) <= 2e-5 * c1
+    A, B = synth.read_solution_file(str(tmp_path / "final.solution")), synth.read_solution_file(str(tmp_path / "resolved.solution"))
+    assert np.array_equal(A["det_xy"], B["det_xy"])          # zero distortion: the device undistortion returns the corners unchanged
+    assert np.abs(A["vec"][-9 * rig.C:] - B["vec"][-9 * rig.C:]).max() == 0      # intrinsics untouched
+
+
+@pytest.mark.gpu
 def test_track_app(host_bins, tmp_path):
     import copy
     rig = copy.copy(synth.make_rig(C=3, M=6, F=20, obs_per_frame=6.0, seed=8))
