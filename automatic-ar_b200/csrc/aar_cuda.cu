@@ -263,7 +263,7 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
     if (!p->opt_f || F <= 0) return AAR_OK;
     LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);      // also feeds k_backsub
     if (n_r > 0 && p->nslots > 0) {
-        const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots * 6 + 255) / 256));
+        const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots + 255) / 256));
         LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
         // two CTAs per SM, at most two full waves (no tail wave), at least a few pipeline stages per CTA

@@ -41,32 +41,40 @@ __global__ void k_frame_chol(DevProblem p, const LmState *__restrict__ st, const
     for (int i = 0; i < 6; i++) dst[21 + i] = y[i];
 }
 
-// One thread per (slot, row i): E_s[i][:] = L^-1 W_s[i][:]^T, and the row's share of b[blk(s)] -= E_s y.
+// One thread per W slot: E_s[i][:] = L^-1 W_s[i][:]^T for its six rows (the 27 doubles of the frame's factor are read once
+// per slot, the slot itself with 16-byte loads / stores), and b[blk(s)] -= E_s y.
 __global__ void __launch_bounds__(256) k_schur_prepare(DevProblem p, long long nslots, const int *__restrict__ slot_frame, const double *__restrict__ fc,
                                                        const double *__restrict__ W, double *__restrict__ E, double *__restrict__ b) {
     extern __shared__ double sb[];   // [n_r] partial b of this CTA
     for (int i = threadIdx.x; i < p.n_r; i += blockDim.x) sb[i] = 0.0;
     __syncthreads();
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < nslots * 6; g += (long long)gridDim.x * blockDim.x) {
-        const long long s = g / 6; const int i = (int)(g % 6);
-        const double *l = fc + (size_t)slot_frame[s] * FC_STRIDE;
-        double x[6];
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
+        const double *lf = fc + (size_t)slot_frame[s] * FC_STRIDE;
+        double l[27];
 #pragma unroll
-        for (int k = 0; k < 6; k++) x[k] = W[(size_t)g * 6 + k];
-        // forward substitution with the packed lower factor
-        int idx = 0; double acc = 0.0;
+        for (int i = 0; i < 27; i++) l[i] = lf[i];
+        const double2 *w2 = reinterpret_cast<const double2 *>(W + (size_t)s * 36);
+        double2 *e2 = reinterpret_cast<double2 *>(E + (size_t)s * 36);
+        double *bs = sb + 6 * p.slot_block[s];
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-            double v = x[r];
+        for (int i = 0; i < 6; i++) {
+            double x[6];
 #pragma unroll
-            for (int k = 0; k < r; k++) v = fma(-l[idx + k], x[k], v);
-            x[r] = v / l[idx + r];
-            idx += r + 1;
-            acc = fma(x[r], l[21 + r], acc);
+            for (int k = 0; k < 3; k++) { const double2 v = w2[i * 3 + k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+            int idx = 0; double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {            // forward substitution with the packed lower factor
+                double v = x[r];
+#pragma unroll
+                for (int k = 0; k < r; k++) v = fma(-l[idx + k], x[k], v);
+                x[r] = v / l[idx + r];
+                idx += r + 1;
+                acc = fma(x[r], l[21 + r], acc);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) e2[i * 3 + k] = make_double2(x[2 * k], x[2 * k + 1]);
+            atomicAdd(bs + i, -acc);
         }
-#pragma unroll
-        for (int k = 0; k < 6; k++) E[(size_t)g * 6 + k] = x[k];
-        atomicAdd(sb + 6 * p.slot_block[s] + i, -acc);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.n_r; i += blockDim.x) if (sb[i] != 0.0) atomicAdd(b + i, sb[i]);
