@@ -92,7 +92,8 @@ struct aar_problem {
     cudaStream_t stream = nullptr; bool own_stream = false;
     DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
-    DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters;
+    DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
+    DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
@@ -169,7 +170,7 @@ void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[
 // the projection kernel needs its 12 warps/SM), so the default is one slab; AAR_JAC_SLABS=n keeps the experiment reachable.
 template <typename JT, int AW>
 int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
-    const size_t tab_bytes = ((size_t)p->C * CAM_TAB + (size_t)p->M * MK_TAB) * sizeof(double);
+    const size_t tab_bytes = (size_t)p->M * MK_TAB * sizeof(double);
     const int tabs_smem = tab_bytes <= 96 * 1024;
     const size_t smem1 = tabs_smem ? tab_bytes : 0;
     auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT, AW>;
@@ -221,6 +222,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
+    if (p->npairs > 0) LAUNCH(p, k_pair_tab, cdiv((long long)p->npairs * PAIR_VARIANTS, 256), 256, 0, p->dp);
     if (Jdump) { if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
     const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -476,6 +478,15 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         const float *xy = d->det_xy + 8 * i;
         raw_a[(size_t)o] = make_float4(xy[0], xy[1], xy[2], xy[3]); raw_b[(size_t)o] = make_float4(xy[4], xy[5], xy[6], xy[7]);
     }
+    // (frame, camera) pairs: runs of consecutive observations in row order; every perturbation of inv(Tc) * To is
+    // evaluated once per pair (k_pair_tab) instead of once per observation
+    std::vector<int> obs_pair((size_t)Nl); std::vector<int2> pair_fc;
+    for (long long o = 0; o < Nl; o++) {
+        const int f = obs_f[(size_t)o], c = obs_cm[(size_t)o] & 0xfff;
+        if (pair_fc.empty() || pair_fc.back().x != f || pair_fc.back().y != c) pair_fc.push_back(make_int2(f, c));
+        obs_pair[(size_t)o] = (int)pair_fc.size() - 1;
+    }
+    p->npairs = (int)pair_fc.size();
     std::vector<double> intr(4 * (size_t)p->C), fixed_c(12 * (size_t)p->C), fixed_m(12 * (size_t)p->M), fixed_f(12 * (size_t)std::max(Fl, 1));
     for (int c = 0; c < p->C; c++) { const double *K = &p->cam_K[9 * (size_t)c]; intr[4 * (size_t)c] = K[0]; intr[4 * (size_t)c + 1] = K[2]; intr[4 * (size_t)c + 2] = K[4]; intr[4 * (size_t)c + 3] = K[5]; pose12_from_T16(&p->cam_T[16 * (size_t)c], &fixed_c[12 * (size_t)c]); }
     for (int m = 0; m < p->M; m++) pose12_from_T16(&p->marker_T[16 * (size_t)m], &fixed_m[12 * (size_t)m]);
@@ -488,7 +499,8 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     UP(p->d_slot_frame, slot_frame); UP(p->d_frame_block_slot, frame_block_slot);
     { std::vector<int> fop((size_t)Fl + 1); for (int f = 0; f <= Fl; f++) fop[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin); UP(p->d_frame_obs_ptr, fop); }
 
-    UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b);
+    UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);
+    CU(p->d_pair_tab.alloc((size_t)std::max(p->npairs, 1) * PAIR_TAB));
     UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
     UP(p->d_cam_fixed, fixed_c); UP(p->d_mk_fixed, fixed_m); UP(p->d_fr_fixed, fixed_f);
 #undef UP
@@ -513,6 +525,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     dp.h = (double)(p->marker_size / 2.f); // aruco::Marker::get3DPoints: half size in float (marker.cpp:358-369)
     dp.J_delta = p->J_delta;
     dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
+    dp.obs_pair = p->d_obs_pair.p; dp.pair_fc = p->d_pair_fc.p; dp.npairs = p->npairs; dp.pair_tab = p->d_pair_tab.p;
     dp.und_a = p->d_und_a.p; dp.und_b = p->d_und_b.p; dp.raw_a = p->d_raw_a.p; dp.raw_b = p->d_raw_b.p;
     dp.intr = p->d_intr.p; dp.frame_slot_ptr = p->d_frame_slot_ptr.p; dp.slot_block = p->d_slot_block.p;
     dp.frame_cs_cum = p->d_frame_cs_cum.p;

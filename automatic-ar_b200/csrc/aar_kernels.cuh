@@ -26,6 +26,10 @@ struct DevProblem {
     const int *obs_f;            // local frame index
     const int *obs_cm;           // cam | marker<<12 | nojac<<31
     const int *obs_slot_c, *obs_slot_m; // W slot of the camera / marker block in this frame, -1 if none
+    const int *obs_pair;         // index of the observation's (frame, camera) pair (runs of consecutive observations in row order)
+    const int2 *pair_fc;         // [npairs] local frame, camera
+    int npairs;
+    double *pair_tab;            // [npairs][PAIR_TAB]: inv(Tc) * To and its perturbed variants (aar_jacobian.cuh: k_pair_tab)
     const float4 *und_a, *und_b, *raw_a, *raw_b; // x0 y0 x1 y1 | x2 y2 x3 y3
     const double *intr;          // [C][4] fx cx fy cy
     // frame CSR of W slots: per frame the camera blocks seen (in order of first appearance), then the marker blocks
