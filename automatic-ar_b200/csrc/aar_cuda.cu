@@ -94,6 +94,7 @@ struct aar_problem {
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
+    DevBuf<int> d_batch_f; int nbatch = 0, win_slots = 0, win_frames = 0; bool acc_mma = false;   // k_jac_accumulate_mma: frame batches
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
@@ -171,9 +172,10 @@ void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[
 template <typename JT, int AW>
 int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
     const size_t tab_bytes = (size_t)p->M * MK_TAB * sizeof(double);
-    const int tabs_smem = tab_bytes <= 96 * 1024;
-    const size_t smem1 = tabs_smem ? tab_bytes : 0;
-    auto k1 = k_jac_project<JT>; auto k2 = k_jac_accumulate<JT, AW>;
+    const int tabs_smem = tab_bytes <= 48 * 1024;          // marker tables of the whole rig next to the per-warp pair buffers
+    const size_t smem1 = (tabs_smem ? tab_bytes : 0) + PROJ_PAIR_SMEM_BYTES;
+    const bool mma = p->acc_mma && slabs == 1;
+    auto k1 = mma ? k_jac_project<JT, true> : k_jac_project<JT, false>; auto k2 = k_jac_accumulate<JT, AW>;
     const size_t scr = (size_t)AW * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
     // as many camera x marker pair accumulators as the shared memory left over by the fixed part (and, when the two
     // kernels share an SM, by the projection kernel's tables) can hold
@@ -199,7 +201,19 @@ int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
         p->launches++;
         if (slabs > 1) { CU(cudaEventRecord(p->ev_slab[done & 15], p->stream)); CU(cudaStreamWaitEvent(s2, p->ev_slab[done & 15], 0)); }
         else prof_mark(p, 9);
-        k2<<<grid2, AW * 32, smem2, s2>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, a, b);
+        if (mma) {
+            // FP64 tensor-core accumulation: frame batches per CTA, frame-keyed blocks leave with plain stores (no zeroing pass needed)
+            auto k3 = k_jac_accumulate_mma<JT>;
+            Acc2Plan q; q.s1 = pl.s1; q.s2 = pl.s2; q.nbatch = p->nbatch; q.win_slots = p->win_slots; q.win_frames = p->win_frames;
+            q.batch_f = p->d_batch_f.p; q.frame_obs_ptr = p->d_frame_obs_ptr.p;
+            const size_t base3 = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
+            q.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, (p->smem_optin - 2048 - base3) / 288);
+            const size_t smem3 = base3 + (size_t)q.hcm_smem * 288;
+            CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            const int grid3 = std::max(1, std::min(p->num_sms, p->nbatch));
+            k3<<<grid3, ACC2_THREADS, smem3, s2>>>(p->dp, q, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+        } else
+            k2<<<grid2, AW * 32, smem2, s2>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, a, b);
         p->launches++;
     }
     if (slabs > 1) {
@@ -229,8 +243,11 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
         const bool exact = p->force_exact_staging || attempt == 1;
         if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
         if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
-        if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
-        if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
+        const bool stores_frame_blocks = p->acc_mma && !(p->jac_slabs > 1 && p->dp.N >= 64LL * 1024 * p->jac_slabs);   // k_jac_accumulate_mma writes every Hf / W entry
+        if (!stores_frame_blocks) {
+            if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
+            if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
+        }
         if (N == 0) return AAR_OK;
         const size_t Np = (N + 31) / 32 * 32;      // whole tiles of 32 observations
         if (p->d_Rv.n < 8 * Np) CU(p->d_Rv.alloc(8 * Np));
@@ -497,7 +514,26 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
     UP(p->d_frame_slot_ptr, slot_ptr); UP(p->d_slot_block, slot_block); UP(p->d_frame_cs_cum, cs_cum);
     UP(p->d_slot_frame, slot_frame); UP(p->d_frame_block_slot, frame_block_slot);
-    { std::vector<int> fop((size_t)Fl + 1); for (int f = 0; f <= Fl; f++) fop[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin); UP(p->d_frame_obs_ptr, fop); }
+    {
+        std::vector<int> fop((size_t)Fl + 1); for (int f = 0; f <= Fl; f++) fop[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin); UP(p->d_frame_obs_ptr, fop);
+        // frame batches of k_jac_accumulate_mma: consecutive frames, at most ACC2_OBS_CAP observations (a single frame may have
+        // more), ACC2_FRAME_CAP frames and slot_cap W slots — a CTA sums the frame-keyed blocks of a batch in shared memory
+        const int slot_cap = std::max(ACC2_SLOT_MIN, p->nrc + p->nrm);
+        std::vector<int> batch_f(1, 0);
+        int co = 0, cs = 0, cf = 0; p->win_slots = 1; p->win_frames = 1;
+        for (int f = 0; f < Fl; f++) {
+            const int no = fop[(size_t)f + 1] - fop[(size_t)f], ns = slot_ptr[(size_t)f + 1] - slot_ptr[(size_t)f];
+            if (cf > 0 && (co + no > ACC2_OBS_CAP || cs + ns > slot_cap || cf + 1 > ACC2_FRAME_CAP)) { batch_f.push_back(f); co = cs = cf = 0; }
+            co += no; cs += ns; cf++;
+            p->win_slots = std::max(p->win_slots, cs); p->win_frames = std::max(p->win_frames, cf);
+        }
+        batch_f.push_back(Fl);
+        p->nbatch = Fl > 0 ? (int)batch_f.size() - 1 : 0;
+        UP(p->d_batch_f, batch_f);
+        const size_t need = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
+        const char *e = getenv("AAR_ACC_MMA");
+        p->acc_mma = need + 2048 <= p->smem_optin && p->win_slots < 65535 && e && *e == '1';   // opt-in: measured on a par with k_jac_accumulate (profiles/r1_notes.md)
+    }
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);
     CU(p->d_pair_tab.alloc((size_t)std::max(p->npairs, 1) * PAIR_TAB));

@@ -90,6 +90,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
+#ifndef AAR_SY_DMMA
+#define AAR_SY_DMMA 1          // 1: mma.sync.m8n8k4.f64 (FP64 tensor cores), 0: per-thread 6x6x6 FMA blocks (round-1 kernel)
+#endif
 #ifndef AAR_SY_MINBLOCKS
 #define AAR_SY_MINBLOCKS 2
 #endif
@@ -127,9 +130,29 @@ __global__ void __launch_bounds__(SY_THREADS, AAR_SY_MINBLOCKS) k_schur_syrk(Dev
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+#if AAR_SY_DMMA
+    // FP64 tensor-core path: the CTA tile is a 96 x 96 x (6 * SY_FB) GEMM per batch, A[m][k] = E_I[i][r] with m = (block, i) of the
+    // row side and k = (frame in batch, r), B[k][n] the same of the column side; absent blocks were zero-filled by cp.async.
+    // 2 x 4 warps, 48 x 24 outputs each = 6 x 3 mma.m8n8k4 tiles (36 accumulators per lane), 6 k-steps per batch:
+    // 9 shared-memory loads per 18 DMMA instead of 36 vector loads per 216 FMAs.
+    const int lane = tid & 31, wm = (tid >> 5) >> 2, wn = (tid >> 5) & 3, g = lane >> 2, q = lane & 3;
+    int offA[6], offB[3], koff[6 * SY_FB / 4];
+#pragma unroll
+    for (int t = 0; t < 6; t++) { const int m = wm * 48 + t * 8 + g; offA[t] = (m / 6) * SY_LD + (m % 6) * 6; }
+#pragma unroll
+    for (int u = 0; u < 3; u++) { const int n = wn * 24 + u * 8 + g; offB[u] = (n / 6) * SY_LD + (n % 6) * 6; }
+#pragma unroll
+    for (int st = 0; st < 6 * SY_FB / 4; st++) { const int k = 4 * st + q; koff[st] = (k / 6) * (SY_TB * SY_LD) + (k % 6); }
+    double cacc[6][3][2];
+#pragma unroll
+    for (int t = 0; t < 6; t++)
+#pragma unroll
+        for (int u = 0; u < 3; u++) { cacc[t][u][0] = 0.0; cacc[t][u][1] = 0.0; }
+#else
     double acc[36];
 #pragma unroll
     for (int i = 0; i < 36; i++) acc[i] = 0.0;
+#endif
     // prologue: slots of batch 0 -> shared, copy of batch 0 in flight, slots of batch 1 in registers
     int slot_next = fetch_slot(0);
     if (idx_thread) (&sPresent[0][0][0][0])[tid] = slot_next;
@@ -144,6 +167,25 @@ __global__ void __launch_bounds__(SY_THREADS, AAR_SY_MINBLOCKS) k_schur_syrk(Dev
         if (b + 1 < nbatch) { issue_copy(nxt); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+#if AAR_SY_DMMA
+        {
+            const double *A0 = &sE[cur][0][0][0], *B0 = &sE[cur][1][0][0];
+#pragma unroll
+            for (int st = 0; st < 6 * SY_FB / 4; st++) {
+                double a[6], bb[3];
+#pragma unroll
+                for (int t = 0; t < 6; t++) a[t] = A0[offA[t] + koff[st]];
+#pragma unroll
+                for (int u = 0; u < 3; u++) bb[u] = B0[offB[u] + koff[st]];
+#pragma unroll
+                for (int t = 0; t < 6; t++)
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(cacc[t][u][0]), "+d"(cacc[t][u][1]) : "d"(a[t]), "d"(bb[u]));
+            }
+        }
+#else
         if (mine) {
             const int nf = min(SY_FB, f1 - (f0 + b * SY_FB));
             for (int ff = 0; ff < nf; ff++) {
@@ -167,8 +209,24 @@ __global__ void __launch_bounds__(SY_THREADS, AAR_SY_MINBLOCKS) k_schur_syrk(Dev
                 }
             }
         }
+#endif
         __syncthreads();
     }
+#if AAR_SY_DMMA
+#pragma unroll
+    for (int t = 0; t < 6; t++)
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int m = wm * 48 + t * 8 + g, n = wn * 24 + u * 8 + 2 * q + e;
+                const int bim = m / 6, bjn = n / 6, gim = ti * SY_TB + bim, gjn = tj * SY_TB + bjn;
+                const double v = cacc[t][u][e];
+                if (gim < nb && gjn < nb && (ti != tj || bim <= bjn) && v != 0.0)
+                    atomicAdd(S + (size_t)(6 * gim + m % 6) * p.n_r + 6 * gjn + n % 6, -v);
+            }
+    (void)mine; (void)bi; (void)bj;
+#else
     if (mine) {
         double *dst = S + (size_t)(6 * gi) * p.n_r + 6 * gj;
 #pragma unroll
@@ -176,6 +234,7 @@ __global__ void __launch_bounds__(SY_THREADS, AAR_SY_MINBLOCKS) k_schur_syrk(Dev
 #pragma unroll
             for (int c = 0; c < 6; c++) if (acc[r * 6 + c] != 0.0) atomicAdd(dst + (size_t)r * p.n_r + c, -acc[r * 6 + c]);
     }
+#endif
 }
 
 } // namespace aar

@@ -279,3 +279,23 @@ def test_exact_staging_fallback_matches(binding, oracle_mod, monkeypatch):
     S64, b64, _ = binding.Problem(rig).reduced_system(z0, 77.0)
     iu = np.triu_indices(len(b32))
     assert np.abs(S32[iu] - S64[iu]).max() <= 1e-13 * np.abs(S64).max() and np.abs(b32 - b64).max() <= 1e-13 * np.abs(b64).max()
+
+
+def test_tensor_core_accumulation_matches_lane_per_observation_kernel(binding, oracle_mod, monkeypatch):
+    """k_jac_accumulate_mma (FP64 tensor cores, warp per observation, frame batches per CTA) and k_jac_accumulate (lane per
+    observation, transposed reductions) sum the same products in different orders: same normal equations to rounding, on a
+    rig with duplicates, an emptied frame, and root camera / marker observations."""
+    rig = small_rig(seed=31, F=120)
+    # duplicated (frame, cam, marker) detections (only the last one has Jacobian rows) and a frame that loses all its rows
+    dup = np.array([5, 40, 41], np.int64)
+    rig.det_frame = np.concatenate([rig.det_frame, rig.det_frame[dup]]); rig.det_cam = np.concatenate([rig.det_cam, rig.det_cam[dup]])
+    rig.det_marker = np.concatenate([rig.det_marker, rig.det_marker[dup]]); rig.det_xy = np.concatenate([rig.det_xy, rig.det_xy[dup] + 0.5])
+    rig.det_marker = rig.det_marker.copy(); rig.det_marker[rig.det_frame == rig.frame_ids[7]] = 99999
+    o = oracle_mod.Oracle(rig); z0 = o.mats2evec()
+    S0, b0, c0 = binding.Problem(rig).reduced_system(z0, 5.0)
+    monkeypatch.setenv("AAR_ACC_MMA", "1")          # opt-in path (profiles/r1_notes.md)
+    S1, b1, c1 = binding.Problem(rig).reduced_system(z0, 5.0)
+    iu = np.triu_indices(len(b1))
+    assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and c1 == c0
+    S_o, b_o, _ = o.reduced_system(z0, 5.0)
+    assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max()

@@ -13,10 +13,12 @@ if a.libs:
     rig = synth.make_config(a.workload, frames=a.frames)
     path = f"/tmp/quick_time_rig_{os.getpid()}.pkl"
     with open(path, "wb") as fh: pickle.dump(rig, fh, protocol=4)
-    for lib in a.libs.split(","):
+    for spec in a.libs.split(","):          # lib[:ENV=value[:ENV=value]]
+        lib, *sets = spec.split(":")
         env = dict(os.environ)
         if lib != "default": env["AAR_LIB"] = os.path.abspath(lib)
-        print(f"== {lib}", flush=True)
+        for kv in sets: env[kv.split("=")[0]] = kv.split("=")[1]
+        print(f"== {spec}", flush=True)
         subprocess.run([sys.executable, __file__, "--workload", a.workload, "--iters", str(a.iters), "--rig", path], env=env)
     os.remove(path)
     sys.exit(0)
