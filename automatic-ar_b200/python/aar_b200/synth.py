@@ -237,7 +237,19 @@ def make_config(name: str, seed=None, frames=None, **kw) -> Rig:
         cfg["F"] = frames
     if seed is None:
         seed = int(name[-1])
-    return make_rig(cfg["C"], cfg["M"], cfg["F"], cfg["obs_per_frame"], seed=seed, **kw)
+    cache = os.environ.get("AAR_RIG_CACHE")          # development aid: several processes of one profiling session share the rig
+    path = os.path.join(cache, f"{name}_{cfg['F']}_{seed}.pkl") if cache and not kw else None
+    if path and os.path.exists(path):
+        import pickle
+        with open(path, "rb") as fh:
+            return pickle.load(fh)
+    rig = make_rig(cfg["C"], cfg["M"], cfg["F"], cfg["obs_per_frame"], seed=seed, **kw)
+    if path:
+        import pickle
+        os.makedirs(cache, exist_ok=True)
+        with open(path, "wb") as fh:
+            pickle.dump(rig, fh, protocol=4)
+    return rig
 
 
 # ------------------------------------------------------------------ dataset files (Appendix A.1/A.2)

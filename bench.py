@@ -37,7 +37,7 @@ for p_ in (os.path.join(ROOT, "automatic-ar_b200", "python"),):
 RESTART = 10            # LM iterations between restarts from z0
 W_J_FLOP = 9.0e3        # algorithmic FP64 flop per marker observation per Jacobian evaluation
 W_PROJ_FLOP = 5912.0    # ... of which in k_jac_project: 37 projections x 152 + 288 for the central differences
-OBS_BYTES = 72          # HBM bytes per marker observation read by k_jac_project (2 x 8 float corners + 8 B indices)
+OBS_BYTES = 76          # HBM bytes per marker observation read by k_jac_project (2 x 8 float corners + 12 B indices; the pair table adds 1536 B per (frame, camera) pair)
 STAGE_BYTES = 640       # HBM bytes per marker observation written by k_jac_project (144 float numerators + 8 double residuals)
 CPU_SAMPLE_FRAMES = 300
 CPU_SAMPLE_ITERS = 3
@@ -299,13 +299,13 @@ def run_ours(args, rank, world, local_rank):
                     "call": f"aar_lm_solve(host io_vec) x{calls}, {chunk} iterations each"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_jac_project (37 pinhole projections per marker observation: residual + quantised central-difference numerators)",
+            "roofline": {"kernel": "k_jac_project (37 pinhole projections per marker observation: residual + quantised central-difference numerators; inv(Tc)*To variants shared per (frame, camera) pair)",
                          "bound": "fp64", "achieved": ach, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["fp64_tflops"],
                          "peak_source": peaks["fp64_src"], "flop_per_marker_obs": W_PROJ_FLOP, "ms_per_launch": jac_ms,
                          "hbm": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"],
                                  "bytes_per_marker_obs": OBS_BYTES + STAGE_BYTES},
                          "traffic": traffic,
-                         "jacobian_phase": {"kernels": "k_jac_project + k_jac_accumulate", "flop_per_marker_obs": W_J_FLOP, "ms": jac_ms + acc_ms,
+                         "jacobian_phase": {"kernels": "k_jac_project + k_jac_accumulate (k_pair_tab, k_expand_jac and the zeroing passes are in phases_ms_per_step.jacobian)", "flop_per_marker_obs": W_J_FLOP, "ms": jac_ms + acc_ms,
                                             "achieved": ach_total, "frac": ach_total / peaks["fp64_tflops"]}},
             "phases_ms_per_step": {k: v / K for k, v in ph.items() if k != "jacobian_launches"}, "total_tries": int(tries_total),
             "setup_s": {"generate": t_gen, "create_upload_undistort": t_create},
