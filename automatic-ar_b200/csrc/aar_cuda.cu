@@ -236,7 +236,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
-    if (p->npairs > 0) LAUNCH(p, k_pair_tab, cdiv((long long)p->npairs * PAIR_VARIANTS, 256), 256, 0, p->dp);
+    if (p->npairs > 0) LAUNCH(p, k_pair_tab, cdiv((long long)p->npairs * PAIR_TAB, 256), 256, 0, p->dp);
     if (Jdump) { if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
     const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
