@@ -95,6 +95,7 @@ struct aar_problem {
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
     DevBuf<int> d_batch_f; int nbatch = 0, win_slots = 0, win_frames = 0; bool acc_mma = false;   // k_jac_accumulate_mma: frame batches
+    DevBuf<int> d_perm_fm, d_perm_cm; bool acc_split = false;                                       // k_acc_frames + k_acc_reduced: visiting orders
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
@@ -201,7 +202,20 @@ int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
         p->launches++;
         if (slabs > 1) { CU(cudaEventRecord(p->ev_slab[done & 15], p->stream)); CU(cudaStreamWaitEvent(s2, p->ev_slab[done & 15], 0)); }
         else prof_mark(p, 9);
-        if (mma) {
+        if (mma && p->acc_split) {
+            // tensor-core accumulation split by key: every sum is visited in an order in which it has runs (aar_jacobian.cuh)
+            auto k4 = k_acc_frames<JT>; auto k5 = k_acc_reduced<JT>;
+            Acc2Plan q; q.s1 = pl.s1; q.s2 = pl.s2; q.nbatch = p->nbatch; q.win_slots = p->win_slots; q.win_frames = p->win_frames; q.hcm_smem = 0;
+            q.batch_f = p->d_batch_f.p; q.frame_obs_ptr = p->d_frame_obs_ptr.p;
+            Acc3Plan pm; pm.perm_fm = p->d_perm_fm.p; pm.perm_cm = p->d_perm_cm.p;
+            const size_t smem4 = ((size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
+            CU(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            const int grid4 = std::max(1, std::min(p->num_sms, p->nbatch));
+            k4<<<grid4, ACC2_THREADS, smem4, s2>>>(p->dp, q, pm, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p);
+            p->launches++;
+            if (p->n_r > 0) k5<<<3 * p->num_sms, ACC3_THREADS, 0, s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
+            else p->launches--;
+        } else if (mma) {
             // FP64 tensor-core accumulation: frame batches per CTA, frame-keyed blocks leave with plain stores (no zeroing pass needed)
             auto k3 = k_jac_accumulate_mma<JT>;
             Acc2Plan q; q.s1 = pl.s1; q.s2 = pl.s2; q.nbatch = p->nbatch; q.win_slots = p->win_slots; q.win_frames = p->win_frames;
@@ -533,6 +547,21 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         const size_t need = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
         const char *e = getenv("AAR_ACC_MMA");
         p->acc_mma = need + 2048 <= p->smem_optin && p->win_slots < 65535 && e && *e == '1';   // opt-in: measured on a par with k_jac_accumulate (profiles/r1_notes.md)
+        p->acc_split = need + 2048 <= p->smem_optin && e && *e == '2';                           // opt-in: k_acc_frames + k_acc_reduced
+        if (p->acc_split) {
+            p->acc_mma = true;        // same row-major staging, same frame batches, Hf / W stored (not accumulated) by the kernel
+            // rows of each frame by (marker, camera); all rows by (camera, marker) — stable, so frames ascend inside a pair
+            std::vector<int> perm_fm((size_t)Nl), perm_cm((size_t)Nl);
+            for (long long o = 0; o < Nl; o++) perm_fm[(size_t)o] = (int)o;
+            auto key_mc = [&](int o) { return ((long long)((obs_cm[(size_t)o] >> 12) & 0x7ffff) << 12) | (obs_cm[(size_t)o] & 0xfff); };
+            for (int f = 0; f < Fl; f++)
+                std::stable_sort(perm_fm.begin() + fop[(size_t)f], perm_fm.begin() + fop[(size_t)f + 1], [&](int a, int b) { return key_mc(a) < key_mc(b); });
+            std::vector<long long> cnt((size_t)p->C * p->M + 1, 0);
+            for (long long o = 0; o < Nl; o++) cnt[(size_t)(obs_cm[(size_t)o] & 0xfff) * p->M + ((obs_cm[(size_t)o] >> 12) & 0x7ffff) + 1]++;
+            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+            for (long long o = 0; o < Nl; o++) perm_cm[(size_t)cnt[(size_t)(obs_cm[(size_t)o] & 0xfff) * p->M + ((obs_cm[(size_t)o] >> 12) & 0x7ffff)]++] = (int)o;
+            UP(p->d_perm_fm, perm_fm); UP(p->d_perm_cm, perm_cm);
+        }
     }
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);

@@ -293,9 +293,10 @@ def test_tensor_core_accumulation_matches_lane_per_observation_kernel(binding, o
     rig.det_marker = rig.det_marker.copy(); rig.det_marker[rig.det_frame == rig.frame_ids[7]] = 99999
     o = oracle_mod.Oracle(rig); z0 = o.mats2evec()
     S0, b0, c0 = binding.Problem(rig).reduced_system(z0, 5.0)
-    monkeypatch.setenv("AAR_ACC_MMA", "1")          # opt-in path (profiles/r1_notes.md)
-    S1, b1, c1 = binding.Problem(rig).reduced_system(z0, 5.0)
-    iu = np.triu_indices(len(b1))
-    assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and c1 == c0
     S_o, b_o, _ = o.reduced_system(z0, 5.0)
-    assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max()
+    iu = np.triu_indices(len(b0))
+    for mode in ("1", "2"):                          # opt-in paths: k_jac_accumulate_mma; k_acc_frames + k_acc_reduced (profiles/r1_notes.md)
+        monkeypatch.setenv("AAR_ACC_MMA", mode)
+        S1, b1, c1 = binding.Problem(rig).reduced_system(z0, 5.0)
+        assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and c1 == c0
+        assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max()
