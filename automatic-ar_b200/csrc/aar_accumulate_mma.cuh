@@ -504,4 +504,301 @@ __global__ void __launch_bounds__(ACC3_THREADS, 3) k_acc_reduced(DevProblem p, A
     emit_pair(); emit_cam();
 }
 
+// k_acc_reduced with the rows of a warp staged through shared memory: k_acc_reduced keeps ONE row in flight per warp and a
+// warp cannot start a row before its data has arrived (600-800 cycles from L2), although the work on a row is ~200 cycles
+// (profiles/r1_notes.md).  Here a warp copies the camera / marker columns and the residual of the next ACC3_ST rows of its list
+// with cp.async (two lanes per row, 16 bytes per copy) while it multiplies the previous ACC3_ST from the other buffer.
+constexpr int ACC3_ST = 16;                 // rows per stage
+template <typename JT> struct Acc3Row { static constexpr int BYTES = 96 * (int)sizeof(JT) + 64; };   // [Jc | Jm] + r
+template <typename JT> constexpr size_t acc3_smem_bytes() { return (size_t)(ACC3_THREADS / 32) * 2 * ACC3_ST * Acc3Row<JT>::BYTES; }
+
+template <typename JT>
+__global__ void __launch_bounds__(ACC3_THREADS, 2) k_acc_reduced_staged(DevProblem p, Acc3Plan pm, double s1, double s2, const JT *__restrict__ Jn, const double *__restrict__ Rv,
+                                                                       double *__restrict__ Hrr, double *__restrict__ gr) {
+    typedef typename Vec2<JT>::type V2;
+    extern __shared__ __align__(16) unsigned char sStage[];
+    constexpr int ROWB = Acc3Row<JT>::BYTES, NCH = ROWB / 16, JCH = 96 * (int)sizeof(JT) / 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    unsigned char *wbuf = sStage + (size_t)warp * 2 * ACC3_ST * ROWB;
+    const long long nwarps = (long long)gridDim.x * (ACC3_THREADS / 32), wid = (long long)blockIdx.x * (ACC3_THREADS / 32) + warp;
+    const long long per = ((p.N + nwarps - 1) / nwarps + ACC3_ST - 1) / ACC3_ST * ACC3_ST;       // whole stages
+    const long long wa = wid * per, wb = min(p.N, wa + per);
+    if (wa >= wb) return;
+    const int n_r = p.n_r;
+    const bool opt_c = p.opt_c != 0, opt_m = p.opt_m != 0;
+    double Tcc[2] = {0, 0}, Tmm[2] = {0, 0}, Tcm[2] = {0, 0};
+    int cur_c = -1, cur_m = -1;
+    auto emit_pair = [&]() {          // Hmm + gm and Hcm of the (camera, marker) run that just ended
+        if (cur_m >= 0 && opt_m && cur_m != p.root_marker) {
+            const int mb = cur_m - (cur_m > p.root_marker ? 1 : 0), bm = 6 * (p.nrc + mb);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = 2 * q + e; const double v = Tmm[e];
+                if (g < 6 && v != 0.0) {
+                    if (j == 6) atomicAdd(gr + bm + g, v * s1);
+                    else if (j < 6 && j >= g) {
+                        atomicAdd(Hrr + (size_t)(bm + g) * n_r + bm + j, v * s2);
+                        if (j != g) atomicAdd(Hrr + (size_t)(bm + j) * n_r + bm + g, v * s2);
+                    }
+                }
+            }
+            if (cur_c >= 0 && opt_c && cur_c != p.root_cam) {
+                const int cb = cur_c - (cur_c > p.root_cam ? 1 : 0);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = 2 * q + e; const double v = Tcm[e];
+                    if (g < 6 && j < 6 && v != 0.0) atomicAdd(Hrr + (size_t)(6 * cb + g) * n_r + 6 * p.nrc + 6 * mb + j, v * s2);
+                }
+            }
+        }
+        Tmm[0] = Tmm[1] = Tcm[0] = Tcm[1] = 0.0;
+    };
+    auto emit_cam = [&]() {           // Hcc + gc of the camera run that just ended
+        if (cur_c >= 0 && opt_c && cur_c != p.root_cam) {
+            const int bc = 6 * (cur_c - (cur_c > p.root_cam ? 1 : 0));
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = 2 * q + e; const double v = Tcc[e];
+                if (g < 6 && v != 0.0) {
+                    if (j == 6) atomicAdd(gr + bc + g, v * s1);
+                    else if (j < 6 && j >= g) {
+                        atomicAdd(Hrr + (size_t)(bc + g) * n_r + bc + j, v * s2);
+                        if (j != g) atomicAdd(Hrr + (size_t)(bc + j) * n_r + bc + g, v * s2);
+                    }
+                }
+            }
+        }
+        Tcc[0] = Tcc[1] = 0.0;
+    };
+    // two lanes per row of a stage: lanes 2r and 2r + 1 hold the index of row r and copy one half of its chunks each
+    const int myrow = lane >> 1, half = lane & 1;
+    auto row_index = [&](long long pos) -> int { const long long my = pos + myrow; return my < wb ? pm.perm_cm[my] : -1; };
+    auto issue = [&](int b, int idx) {
+        if (idx >= 0) {
+            const char *srcJ = reinterpret_cast<const char *>(Jn + (size_t)idx * 144), *srcR = reinterpret_cast<const char *>(Rv + (size_t)idx * 8);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + ((size_t)b * ACC3_ST + myrow) * ROWB);
+#pragma unroll
+            for (int k = 0; k < NCH / 2; k++) {
+                const int c = half * (NCH / 2) + k;
+                const char *src = c < JCH ? srcJ + 16 * c : srcR + 16 * (c - JCH);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int idx_cur = row_index(wa);
+    int cm_cur = idx_cur >= 0 ? p.obs_cm[idx_cur] : (int)0x80000000u;
+    issue(0, idx_cur);
+    int idx_nxt = row_index(wa + ACC3_ST);
+    int stage = 0;
+    for (long long pos = wa; pos < wb; pos += ACC3_ST, stage ^= 1) {
+        const int cm_nxt = idx_nxt >= 0 ? p.obs_cm[idx_nxt] : (int)0x80000000u;
+        issue(stage ^ 1, idx_nxt);                                     // the next stage's rows in flight while this stage is multiplied
+        const int idx_nn = row_index(pos + 2 * ACC3_ST);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const int cnt = (int)min((long long)ACC3_ST, wb - pos);
+        const unsigned char *sb = wbuf + (size_t)stage * ACC3_ST * ROWB;
+        for (int t = 0; t < cnt; t++) {
+            const int cm = __shfl_sync(0xffffffffu, cm_cur, 2 * t);
+            const unsigned char *row = sb + (size_t)t * ROWB;
+            V2 xc, xm; double2 rr;
+            xc.x = xc.y = xm.x = xm.y = (JT)0; rr.x = rr.y = 0.0;
+            if (g < 6) { xc = *reinterpret_cast<const V2 *>(row + (g * 8 + 2 * q) * sizeof(JT)); xm = *reinterpret_cast<const V2 *>(row + (48 + g * 8 + 2 * q) * sizeof(JT)); }
+            else if (g == 6) rr = *reinterpret_cast<const double2 *>(row + 96 * sizeof(JT) + 16 * q);
+            const int c = obs_cam(cm), m = obs_marker(cm);
+            if (c != cur_c || m != cur_m) {
+                emit_pair();
+                if (c != cur_c) { emit_cam(); cur_c = c; }
+                cur_m = m;
+            }
+            const bool use = !obs_nojac(cm), uc = use && opt_c && c != p.root_cam, um = use && opt_m && m != p.root_marker;
+            if (!(uc && um)) {                       // stale columns: the projection kernel does not write what has no Jacobian
+                if (!uc) { xc.x = (JT)0; xc.y = (JT)0; }
+                if (!um) { xm.x = (JT)0; xm.y = (JT)0; }
+                if (!use) { rr.x = 0.0; rr.y = 0.0; }
+            }
+            const double ac0 = (double)xc.x, ac1 = (double)xc.y, am0 = (double)xm.x, am1 = (double)xm.y;
+            const double bcr0 = g == 6 ? rr.x : ac0, bcr1 = g == 6 ? rr.y : ac1, bmr0 = g == 6 ? rr.x : am0, bmr1 = g == 6 ? rr.y : am1;   // [Jc | r], [Jm | r]
+            if (opt_c) { dmma884(Tcc, ac0, bcr0); dmma884(Tcc, ac1, bcr1); }
+            if (opt_m) { dmma884(Tmm, am0, bmr0); dmma884(Tmm, am1, bmr1); }
+            if (opt_c && opt_m) { dmma884(Tcm, ac0, am0); dmma884(Tcm, ac1, am1); }
+        }
+        __syncwarp();                                                  // everyone is done with this buffer before it is refilled
+        cm_cur = cm_nxt; idx_nxt = idx_nn;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    emit_pair(); emit_cam();
+}
+
+// k_acc_frames with the same staging (float32 numerators only; the FP64-staging fallback keeps k_acc_frames): per warp two
+// buffers of ACCF_ST rows — phase A copies [Jc | Jf | r] of consecutive rows, phase B [Jm | Jf] of the rows its permutation names.
+constexpr int ACCF_ST = 8, ACCF_ROWB = 448;       // rows per stage (4 lanes copy one row), bytes per staged row
+constexpr size_t accf_stage_bytes() { return (size_t)ACC2_WARPS * 2 * ACCF_ST * ACCF_ROWB; }
+
+__global__ void __launch_bounds__(ACC2_THREADS, 1) k_acc_frames_staged(DevProblem p, Acc2Plan pl, Acc3Plan pm, const float *__restrict__ Jn, const double *__restrict__ Rv,
+                                                                      double *__restrict__ Hf, double *__restrict__ W) {
+    extern __shared__ __align__(16) double sAcc[];
+    double *sW = sAcc;                                                        // [win_slots][36]  W blocks of the current batch
+    double *sHf = sW + (size_t)pl.win_slots * 36;                             // [win_frames][27] frame blocks of the current batch
+    const int n_all = pl.win_slots * 36 + pl.win_frames * 27;
+    unsigned char *sStage = reinterpret_cast<unsigned char *>(sAcc + ((n_all + 1) & ~1));          // 16-byte aligned
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    unsigned char *wbuf = sStage + (size_t)warp * 2 * ACCF_ST * ACCF_ROWB;
+    for (int i = tid; i < n_all; i += ACC2_THREADS) sAcc[i] = 0.0;
+    __syncthreads();
+    const double s1 = pl.s1, s2 = pl.s2;
+    const unsigned aW = (unsigned)__cvta_generic_to_shared(sW), aHf = (unsigned)__cvta_generic_to_shared(sHf);
+    unsigned eW[2], eHf[2]; int m36[2], m27[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const int j = 2 * q + e;
+        const int idx36 = (g < 6 && j < 6) ? g * 6 + j : -1;
+        const int idxU = (g < 6 && j < 6 && j >= g) ? g * 6 - g * (g - 1) / 2 + (j - g) : -1;
+        const int idx27 = idxU >= 0 ? idxU : ((g < 6 && j == 6) ? 21 + g : -1);
+        m36[e] = idx36 >= 0; m27[e] = idx27 >= 0;
+        eW[e] = aW + 8u * max(idx36, 0); eHf[e] = aHf + 8u * max(idx27, 0);
+    }
+    const bool opt_c = p.opt_c != 0, opt_m = p.opt_m != 0, opt_f = p.opt_f != 0;
+    auto add_W = [&](int slot_rel, const double (&T)[2]) {      // a finished 6x6 W block into the window
+        unsigned ad[2]; double val[2]; int on[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) { ad[e] = eW[e] + 8u * 36u * max(slot_rel, 0); on[e] = m36[e] & (slot_rel >= 0); val[e] = T[e]; }
+        smem_add_batch<2>(ad, val, on);
+    };
+    const int myrow = lane >> 2, part = lane & 3;            // four lanes per staged row
+    for (int b = blockIdx.x; b < pl.nbatch; b += gridDim.x) {
+        const int f0 = pl.batch_f[b], f1 = pl.batch_f[b + 1];
+        const int o0 = pl.frame_obs_ptr[f0], o1 = pl.frame_obs_ptr[f1];
+        const int sl0 = p.frame_slot_ptr[f0], sl1 = p.frame_slot_ptr[f1];
+        const int per = ((o1 - o0 + ACC2_WARPS - 1) / ACC2_WARPS + ACCF_ST - 1) / ACCF_ST * ACCF_ST;      // whole stages
+        const int wa = o0 + warp * per, wb = min(o1, wa + per);
+        if (wa < wb && opt_f) {
+            // ---------------- phase A: row order.  Hff + gf = Jf^T [Jf | r] over the frame run, W_c = Jc^T Jf over the (frame, camera) run
+            {
+                double Tff[2] = {0, 0}, Tcf[2] = {0, 0};
+                int cur_f = -1, cur_c = -1, cur_slc = -1;
+                auto emit_cam = [&]() { if (cur_slc >= 0) add_W(cur_slc, Tcf); Tcf[0] = Tcf[1] = 0.0; };
+                auto emit_frame = [&]() {
+                    if (cur_f >= 0) {
+                        unsigned ad[2]; double val[2]; int on[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) { ad[e] = eHf[e] + 8u * 27u * (cur_f - f0); on[e] = m27[e]; val[e] = Tff[e]; }
+                        smem_add_batch<2>(ad, val, on);
+                    }
+                    Tff[0] = Tff[1] = 0.0;
+                };
+                auto issue = [&](int bsel, int pos) {          // [Jc | Jf | r] of rows pos .. pos + ACCF_ST - 1: 28 chunks of 16 bytes per row, 7 per lane
+                    const int o = pos + myrow;
+                    if (o < wb) {
+                        const char *srcJ = reinterpret_cast<const char *>(Jn + (size_t)o * 144), *srcR = reinterpret_cast<const char *>(Rv + (size_t)o * 8);
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + ((size_t)bsel * ACCF_ST + myrow) * ACCF_ROWB);
+#pragma unroll
+                        for (int k = 0; k < 7; k++) {
+                            const int c = part * 7 + k;
+                            const char *src = c < 12 ? srcJ + 16 * c : (c < 24 ? srcJ + 384 + 16 * (c - 12) : srcR + 16 * (c - 24));
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                auto meta = [&](int pos, int &cm, int &f, int &slc) {          // held by the four lanes of row pos + myrow
+                    const int o = pos + myrow;
+                    cm = (int)0x80000000u; f = 0; slc = -1;
+                    if (o < wb) { cm = p.obs_cm[o]; f = p.obs_f[o]; const int a = p.obs_slot_c[o]; slc = a >= 0 ? a - sl0 : -1; }
+                };
+                int cm_cur, f_cur, sl_cur, cm_nxt, f_nxt, sl_nxt;
+                meta(wa, cm_cur, f_cur, sl_cur);
+                issue(0, wa);
+                int stage = 0;
+                for (int pos = wa; pos < wb; pos += ACCF_ST, stage ^= 1) {
+                    meta(pos + ACCF_ST, cm_nxt, f_nxt, sl_nxt);
+                    issue(stage ^ 1, pos + ACCF_ST);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    __syncwarp();
+                    const int cnt = min(ACCF_ST, wb - pos);
+                    const unsigned char *sb = wbuf + (size_t)stage * ACCF_ST * ACCF_ROWB;
+                    for (int t = 0; t < cnt; t++) {
+                        const int cm = __shfl_sync(0xffffffffu, cm_cur, 4 * t), f = __shfl_sync(0xffffffffu, f_cur, 4 * t), slc = __shfl_sync(0xffffffffu, sl_cur, 4 * t);
+                        const unsigned char *row = sb + (size_t)t * ACCF_ROWB;
+                        float2 xc = make_float2(0.f, 0.f), xf = make_float2(0.f, 0.f); double2 rr = make_double2(0.0, 0.0);
+                        if (g < 6) { xc = *reinterpret_cast<const float2 *>(row + (g * 8 + 2 * q) * 4); xf = *reinterpret_cast<const float2 *>(row + 192 + (g * 8 + 2 * q) * 4); }
+                        else if (g == 6) rr = *reinterpret_cast<const double2 *>(row + 384 + 16 * q);
+                        const int c = obs_cam(cm);
+                        if (f != cur_f || c != cur_c) {
+                            emit_cam();
+                            if (f != cur_f) { emit_frame(); cur_f = f; }
+                            cur_c = c; cur_slc = slc;
+                        }
+                        const bool use = !obs_nojac(cm), uc = use && opt_c && c != p.root_cam;
+                        if (!uc) { xc.x = 0.f; xc.y = 0.f; if (!use) { xf.x = 0.f; xf.y = 0.f; rr.x = 0.0; rr.y = 0.0; } }
+                        const double ac0 = (double)xc.x, ac1 = (double)xc.y, af0 = (double)xf.x, af1 = (double)xf.y;
+                        const double bfr0 = g == 6 ? rr.x : af0, bfr1 = g == 6 ? rr.y : af1;        // [Jf | r]
+                        dmma884(Tff, af0, bfr0); dmma884(Tff, af1, bfr1);
+                        if (opt_c) { dmma884(Tcf, ac0, af0); dmma884(Tcf, ac1, af1); }
+                    }
+                    __syncwarp();
+                    cm_cur = cm_nxt; f_cur = f_nxt; sl_cur = sl_nxt;
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                emit_cam(); emit_frame();
+            }
+            // ---------------- phase B: the same rows in (marker, camera) order inside each frame.  W_m = Jm^T Jf over the (frame, marker) run
+            if (opt_m) {
+                double Tmf[2] = {0, 0};
+                int cur_slm = -1;
+                auto meta = [&](int pos, int &o, int &cm, int &slm) {
+                    const int i = pos + myrow;
+                    o = -1; cm = (int)0x80000000u; slm = -1;
+                    if (i < wb) { o = pm.perm_fm[i]; cm = p.obs_cm[o]; const int a = p.obs_slot_m[o]; slm = a >= 0 ? a - sl0 : -1; }
+                };
+                auto issue = [&](int bsel, int o) {            // [Jm | Jf] = bytes 192 .. 575 of the row: 24 chunks, 6 per lane
+                    if (o >= 0) {
+                        const char *srcJ = reinterpret_cast<const char *>(Jn + (size_t)o * 144) + 192;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + ((size_t)bsel * ACCF_ST + myrow) * ACCF_ROWB);
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            const int c = part * 6 + k;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(srcJ + 16 * c) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                __syncwarp();                                  // phase A's last reads of the buffers are over
+                int o_cur, cm_cur, sl_cur, o_nxt, cm_nxt, sl_nxt;
+                meta(wa, o_cur, cm_cur, sl_cur);
+                issue(0, o_cur);
+                int stage = 0;
+                for (int pos = wa; pos < wb; pos += ACCF_ST, stage ^= 1) {
+                    meta(pos + ACCF_ST, o_nxt, cm_nxt, sl_nxt);
+                    issue(stage ^ 1, o_nxt);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    __syncwarp();
+                    const int cnt = min(ACCF_ST, wb - pos);
+                    const unsigned char *sb = wbuf + (size_t)stage * ACCF_ST * ACCF_ROWB;
+                    for (int t = 0; t < cnt; t++) {
+                        const int cm = __shfl_sync(0xffffffffu, cm_cur, 4 * t), slm = __shfl_sync(0xffffffffu, sl_cur, 4 * t);
+                        const unsigned char *row = sb + (size_t)t * ACCF_ROWB;
+                        float2 xm = make_float2(0.f, 0.f), xf = make_float2(0.f, 0.f);
+                        if (g < 6) { xm = *reinterpret_cast<const float2 *>(row + (g * 8 + 2 * q) * 4); xf = *reinterpret_cast<const float2 *>(row + 192 + (g * 8 + 2 * q) * 4); }
+                        if (slm != cur_slm) { if (cur_slm >= 0) add_W(cur_slm, Tmf); Tmf[0] = Tmf[1] = 0.0; cur_slm = slm; }
+                        const bool um = !obs_nojac(cm) && obs_marker(cm) != p.root_marker;
+                        if (!um) { xm.x = 0.f; xm.y = 0.f; if (obs_nojac(cm)) { xf.x = 0.f; xf.y = 0.f; } }      // rows of erased duplicates are never written
+                        dmma884(Tmf, (double)xm.x, (double)xf.x); dmma884(Tmf, (double)xm.y, (double)xf.y);
+                    }
+                    __syncwarp();
+                    o_cur = o_nxt; cm_cur = cm_nxt; sl_cur = sl_nxt;
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (cur_slm >= 0) add_W(cur_slm, Tmf);
+            }
+        }
+        __syncthreads();
+        // the batch's frame-keyed blocks are complete: plain coalesced stores, and the windows are cleared for the next batch
+        for (int i = tid; i < (sl1 - sl0) * 36; i += ACC2_THREADS) { W[(size_t)sl0 * 36 + i] = sW[i] * s2; sW[i] = 0.0; }
+        for (int i = tid; i < (f1 - f0) * 27; i += ACC2_THREADS) { Hf[(size_t)f0 * HF_STRIDE + i] = sHf[i] * ((i % 27) < 21 ? s2 : s1); sHf[i] = 0.0; }
+        __syncthreads();
+    }
+}
+
 } // namespace aar

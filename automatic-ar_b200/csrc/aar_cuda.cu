@@ -95,7 +95,7 @@ struct aar_problem {
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
     DevBuf<int> d_batch_f; int nbatch = 0, win_slots = 0, win_frames = 0; bool acc_mma = false;   // k_jac_accumulate_mma: frame batches
-    DevBuf<int> d_perm_fm, d_perm_cm; bool acc_split = false;                                       // k_acc_frames + k_acc_reduced: visiting orders
+    DevBuf<int> d_perm_fm, d_perm_cm; bool acc_split = false, acc_staged = false, acc_staged_frames = false;                                       // k_acc_frames + k_acc_reduced: visiting orders
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
@@ -211,9 +211,18 @@ int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
             const size_t smem4 = ((size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
             CU(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             const int grid4 = std::max(1, std::min(p->num_sms, p->nbatch));
-            k4<<<grid4, ACC2_THREADS, smem4, s2>>>(p->dp, q, pm, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p);
+            const size_t win_doubles = (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27, smem4s = ((win_doubles + 1) & ~(size_t)1) * sizeof(double) + accf_stage_bytes();
+            if (p->acc_staged_frames && sizeof(JT) == 4 && smem4s + 2048 <= p->smem_optin) {
+                CU(cudaFuncSetAttribute(k_acc_frames_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4s));
+                k_acc_frames_staged<<<grid4, ACC2_THREADS, smem4s, s2>>>(p->dp, q, pm, reinterpret_cast<const float *>(Jn), p->d_Rv.p, p->d_Hf.p, p->d_W.p);
+            } else
+                k4<<<grid4, ACC2_THREADS, smem4, s2>>>(p->dp, q, pm, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p);
             p->launches++;
-            if (p->n_r > 0) k5<<<3 * p->num_sms, ACC3_THREADS, 0, s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
+            if (p->n_r > 0 && p->acc_staged) {
+                auto k6 = k_acc_reduced_staged<JT>;
+                CU(cudaFuncSetAttribute(k6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc3_smem_bytes<JT>()));
+                k6<<<2 * p->num_sms, ACC3_THREADS, acc3_smem_bytes<JT>(), s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
+            } else if (p->n_r > 0) k5<<<3 * p->num_sms, ACC3_THREADS, 0, s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
             else p->launches--;
         } else if (mma) {
             // FP64 tensor-core accumulation: frame batches per CTA, frame-keyed blocks leave with plain stores (no zeroing pass needed)
@@ -547,7 +556,9 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         const size_t need = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
         const char *e = getenv("AAR_ACC_MMA");
         p->acc_mma = need + 2048 <= p->smem_optin && p->win_slots < 65535 && e && *e == '1';   // opt-in: measured on a par with k_jac_accumulate (profiles/r1_notes.md)
-        p->acc_split = need + 2048 <= p->smem_optin && e && *e == '2';                           // opt-in: k_acc_frames + k_acc_reduced
+        p->acc_split = need + 2048 <= p->smem_optin && e && (*e == '2' || *e == '3' || *e == '4');            // opt-in: k_acc_frames + k_acc_reduced
+        p->acc_staged = p->acc_split && (*e == '3' || *e == '4');                                // ... with k_acc_reduced_staged
+        p->acc_staged_frames = p->acc_split && *e == '4';                                         // ... and k_acc_frames_staged
         if (p->acc_split) {
             p->acc_mma = true;        // same row-major staging, same frame batches, Hf / W stored (not accumulated) by the kernel
             // rows of each frame by (marker, camera); all rows by (camera, marker) — stable, so frames ascend inside a pair
