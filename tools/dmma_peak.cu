@@ -32,4 +32,6 @@ template <int NACC> void run(int ctas_per_sm) {
     printf("{\"instr\": \"mma.sync.m8n8k4.f64\", \"independent_accumulators\": %d, \"warps_per_sm\": %d, \"ms\": %.3f, \"tflops\": %.2f}\n", NACC, 8 * ctas_per_sm, ms, flop / ms * 1e-9);
     cudaFree(d);
 }
-int main() { run<4>(1); run<8>(1); run<8>(2); run<16>(2); run<16>(4); return 0; }
+// 1 or 2 accumulators per warp at 8 warps/SM (2 per scheduler): the rate then measures the dependent-issue latency of the
+// instruction — what a kernel pays when consecutive observations chain on the same accumulator (profiles/r1_notes.md)
+int main() { run<1>(1); run<2>(1); run<4>(1); run<8>(1); run<8>(2); run<16>(2); run<16>(4); return 0; }
