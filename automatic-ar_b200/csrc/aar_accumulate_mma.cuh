@@ -509,6 +509,12 @@ __global__ void __launch_bounds__(ACC3_THREADS, 3) k_acc_reduced(DevProblem p, A
 // (profiles/r1_notes.md).  Here a warp copies the camera / marker columns and the residual of the next ACC3_ST rows of its list
 // with cp.async (two lanes per row, 16 bytes per copy) while it multiplies the previous ACC3_ST from the other buffer.
 constexpr int ACC3_ST = 16;                 // rows per stage
+#ifndef AAR_DMMA_TWO_SETS
+// 1: the two k-steps of a row go to two accumulator sets that are added when a run ends, so that no DMMA waits for the one
+// issued just before it (SASS of the kernel below: a row is two DEPENDENT DMMAs per product followed by register moves that
+// wait for them).  Written at the very end of round 1 without GPU time left to measure it: off, k_acc_reduced_staged only.
+#define AAR_DMMA_TWO_SETS 0
+#endif
 template <typename JT> struct Acc3Row { static constexpr int BYTES = 96 * (int)sizeof(JT) + 64; };   // [Jc | Jm] + r
 template <typename JT> constexpr size_t acc3_smem_bytes() { return (size_t)(ACC3_THREADS / 32) * 2 * ACC3_ST * Acc3Row<JT>::BYTES; }
 
@@ -527,8 +533,14 @@ __global__ void __launch_bounds__(ACC3_THREADS, 2) k_acc_reduced_staged(DevProbl
     const int n_r = p.n_r;
     const bool opt_c = p.opt_c != 0, opt_m = p.opt_m != 0;
     double Tcc[2] = {0, 0}, Tmm[2] = {0, 0}, Tcm[2] = {0, 0};
+#if AAR_DMMA_TWO_SETS
+    double Ucc[2] = {0, 0}, Umm[2] = {0, 0}, Ucm[2] = {0, 0};       // second k-step of every row: no DMMA depends on the one before it
+#endif
     int cur_c = -1, cur_m = -1;
     auto emit_pair = [&]() {          // Hmm + gm and Hcm of the (camera, marker) run that just ended
+#if AAR_DMMA_TWO_SETS
+        Tmm[0] += Umm[0]; Tmm[1] += Umm[1]; Tcm[0] += Ucm[0]; Tcm[1] += Ucm[1]; Umm[0] = Umm[1] = Ucm[0] = Ucm[1] = 0.0;
+#endif
         if (cur_m >= 0 && opt_m && cur_m != p.root_marker) {
             const int mb = cur_m - (cur_m > p.root_marker ? 1 : 0), bm = 6 * (p.nrc + mb);
 #pragma unroll
@@ -554,6 +566,9 @@ __global__ void __launch_bounds__(ACC3_THREADS, 2) k_acc_reduced_staged(DevProbl
         Tmm[0] = Tmm[1] = Tcm[0] = Tcm[1] = 0.0;
     };
     auto emit_cam = [&]() {           // Hcc + gc of the camera run that just ended
+#if AAR_DMMA_TWO_SETS
+        Tcc[0] += Ucc[0]; Tcc[1] += Ucc[1]; Ucc[0] = Ucc[1] = 0.0;
+#endif
         if (cur_c >= 0 && opt_c && cur_c != p.root_cam) {
             const int bc = 6 * (cur_c - (cur_c > p.root_cam ? 1 : 0));
 #pragma unroll
@@ -620,9 +635,15 @@ __global__ void __launch_bounds__(ACC3_THREADS, 2) k_acc_reduced_staged(DevProbl
             }
             const double ac0 = (double)xc.x, ac1 = (double)xc.y, am0 = (double)xm.x, am1 = (double)xm.y;
             const double bcr0 = g == 6 ? rr.x : ac0, bcr1 = g == 6 ? rr.y : ac1, bmr0 = g == 6 ? rr.x : am0, bmr1 = g == 6 ? rr.y : am1;   // [Jc | r], [Jm | r]
+#if AAR_DMMA_TWO_SETS
+            if (opt_c) { dmma884(Tcc, ac0, bcr0); dmma884(Ucc, ac1, bcr1); }
+            if (opt_m) { dmma884(Tmm, am0, bmr0); dmma884(Umm, am1, bmr1); }
+            if (opt_c && opt_m) { dmma884(Tcm, ac0, am0); dmma884(Ucm, ac1, am1); }
+#else
             if (opt_c) { dmma884(Tcc, ac0, bcr0); dmma884(Tcc, ac1, bcr1); }
             if (opt_m) { dmma884(Tmm, am0, bmr0); dmma884(Tmm, am1, bmr1); }
             if (opt_c && opt_m) { dmma884(Tcm, ac0, am0); dmma884(Tcm, ac1, am1); }
+#endif
         }
         __syncwarp();                                                  // everyone is done with this buffer before it is refilled
         cm_cur = cm_nxt; idx_nxt = idx_nn;
