@@ -512,7 +512,7 @@ constexpr int ACC3_ST = 16;                 // rows per stage
 #ifndef AAR_DMMA_TWO_SETS
 // 1: the two k-steps of a row go to two accumulator sets that are added when a run ends, so that no DMMA waits for the one
 // issued just before it (SASS of the kernel below: a row is two DEPENDENT DMMAs per product followed by register moves that
-// wait for them).  Written at the very end of round 1 without GPU time left to measure it: off, k_acc_reduced_staged only.
+// wait for them).  Written at the very end of round 1 without GPU time left to measure it: off; in k_acc_reduced_staged and k_acc_frames_staged.
 #define AAR_DMMA_TWO_SETS 0
 #endif
 template <typename JT> struct Acc3Row { static constexpr int BYTES = 96 * (int)sizeof(JT) + 64; };   // [Jc | Jm] + r
@@ -698,9 +698,21 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_acc_frames_staged(DevProble
             // ---------------- phase A: row order.  Hff + gf = Jf^T [Jf | r] over the frame run, W_c = Jc^T Jf over the (frame, camera) run
             {
                 double Tff[2] = {0, 0}, Tcf[2] = {0, 0};
+#if AAR_DMMA_TWO_SETS
+                double Uff[2] = {0, 0}, Ucf[2] = {0, 0};
+#endif
                 int cur_f = -1, cur_c = -1, cur_slc = -1;
-                auto emit_cam = [&]() { if (cur_slc >= 0) add_W(cur_slc, Tcf); Tcf[0] = Tcf[1] = 0.0; };
+                auto emit_cam = [&]() {
+#if AAR_DMMA_TWO_SETS
+                    Tcf[0] += Ucf[0]; Tcf[1] += Ucf[1]; Ucf[0] = Ucf[1] = 0.0;
+#endif
+                    if (cur_slc >= 0) add_W(cur_slc, Tcf);
+                    Tcf[0] = Tcf[1] = 0.0;
+                };
                 auto emit_frame = [&]() {
+#if AAR_DMMA_TWO_SETS
+                    Tff[0] += Uff[0]; Tff[1] += Uff[1]; Uff[0] = Uff[1] = 0.0;
+#endif
                     if (cur_f >= 0) {
                         unsigned ad[2]; double val[2]; int on[2];
 #pragma unroll
@@ -755,8 +767,13 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_acc_frames_staged(DevProble
                         if (!uc) { xc.x = 0.f; xc.y = 0.f; if (!use) { xf.x = 0.f; xf.y = 0.f; rr.x = 0.0; rr.y = 0.0; } }
                         const double ac0 = (double)xc.x, ac1 = (double)xc.y, af0 = (double)xf.x, af1 = (double)xf.y;
                         const double bfr0 = g == 6 ? rr.x : af0, bfr1 = g == 6 ? rr.y : af1;        // [Jf | r]
+#if AAR_DMMA_TWO_SETS
+                        dmma884(Tff, af0, bfr0); dmma884(Uff, af1, bfr1);
+                        if (opt_c) { dmma884(Tcf, ac0, af0); dmma884(Ucf, ac1, af1); }
+#else
                         dmma884(Tff, af0, bfr0); dmma884(Tff, af1, bfr1);
                         if (opt_c) { dmma884(Tcf, ac0, af0); dmma884(Tcf, ac1, af1); }
+#endif
                     }
                     __syncwarp();
                     cm_cur = cm_nxt; f_cur = f_nxt; sl_cur = sl_nxt;
@@ -767,6 +784,9 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_acc_frames_staged(DevProble
             // ---------------- phase B: the same rows in (marker, camera) order inside each frame.  W_m = Jm^T Jf over the (frame, marker) run
             if (opt_m) {
                 double Tmf[2] = {0, 0};
+#if AAR_DMMA_TWO_SETS
+                double Umf[2] = {0, 0};
+#endif
                 int cur_slm = -1;
                 auto meta = [&](int pos, int &o, int &cm, int &slm) {
                     const int i = pos + myrow;
@@ -802,15 +822,28 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_acc_frames_staged(DevProble
                         const unsigned char *row = sb + (size_t)t * ACCF_ROWB;
                         float2 xm = make_float2(0.f, 0.f), xf = make_float2(0.f, 0.f);
                         if (g < 6) { xm = *reinterpret_cast<const float2 *>(row + (g * 8 + 2 * q) * 4); xf = *reinterpret_cast<const float2 *>(row + 192 + (g * 8 + 2 * q) * 4); }
-                        if (slm != cur_slm) { if (cur_slm >= 0) add_W(cur_slm, Tmf); Tmf[0] = Tmf[1] = 0.0; cur_slm = slm; }
+                        if (slm != cur_slm) {
+#if AAR_DMMA_TWO_SETS
+                            Tmf[0] += Umf[0]; Tmf[1] += Umf[1]; Umf[0] = Umf[1] = 0.0;
+#endif
+                            if (cur_slm >= 0) add_W(cur_slm, Tmf);
+                            Tmf[0] = Tmf[1] = 0.0; cur_slm = slm;
+                        }
                         const bool um = !obs_nojac(cm) && obs_marker(cm) != p.root_marker;
                         if (!um) { xm.x = 0.f; xm.y = 0.f; if (obs_nojac(cm)) { xf.x = 0.f; xf.y = 0.f; } }      // rows of erased duplicates are never written
+#if AAR_DMMA_TWO_SETS
+                        dmma884(Tmf, (double)xm.x, (double)xf.x); dmma884(Umf, (double)xm.y, (double)xf.y);
+#else
                         dmma884(Tmf, (double)xm.x, (double)xf.x); dmma884(Tmf, (double)xm.y, (double)xf.y);
+#endif
                     }
                     __syncwarp();
                     o_cur = o_nxt; cm_cur = cm_nxt; sl_cur = sl_nxt;
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if AAR_DMMA_TWO_SETS
+                Tmf[0] += Umf[0]; Tmf[1] += Umf[1];
+#endif
                 if (cur_slm >= 0) add_W(cur_slm, Tmf);
             }
         }
