@@ -298,5 +298,5 @@ def test_tensor_core_accumulation_matches_lane_per_observation_kernel(binding, o
     for mode in ("1", "2", "4"):                     # opt-in paths: k_jac_accumulate_mma; k_acc_frames + k_acc_reduced; the same, rows staged (profiles/r1_notes.md)
         monkeypatch.setenv("AAR_ACC_MMA", mode)
         S1, b1, c1 = binding.Problem(rig).reduced_system(z0, 5.0)
-        assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and c1 == c0
+        assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and abs(c1 - c0) <= 1e-13 * c0
         assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max()
