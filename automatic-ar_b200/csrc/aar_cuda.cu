@@ -172,7 +172,7 @@ void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[
 // the projection kernel needs its 12 warps/SM), so the default is one slab; AAR_JAC_SLABS=n keeps the experiment reachable.
 template <typename JT, int AW>
 int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
-    const size_t tab_bytes = (size_t)p->M * MK_TAB * sizeof(double);
+    const size_t tab_bytes = (size_t)((p->M * MK_TAB_S + 1) & ~1) * sizeof(double);
     const int tabs_smem = tab_bytes <= 48 * 1024;          // marker tables of the whole rig next to the per-warp pair buffers
     const size_t smem1 = (tabs_smem ? tab_bytes : 0) + PROJ_PAIR_SMEM_BYTES;
     const bool mma = p->acc_mma && slabs == 1;
@@ -799,11 +799,12 @@ int aar_eval_residual(aar_problem *p, const double *z, float huber_delta, double
 int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t *rowidx, double *vals) {
     if (!p || !z || !colptr || !rowidx || !vals) return AAR_ERR_INVALID;
     if (p->world != 1) { set_err("aar_eval_jacobian: single-rank handles only"); return AAR_ERR_INVALID; }
+    if (p->lm_active) { set_err("aar_eval_jacobian between aar_lm_begin and aar_lm_end would replace the resident iterate"); return AAR_ERR_INVALID; }
     CU(cudaSetDevice(p->device));
     int rc = upload_z(p, z, p->d_z.p); if (rc) return rc;
     const size_t nj = 144 * (size_t)std::max<long long>(p->N, 1);
     if (p->d_J.n < nj) CU(p->d_J.alloc(nj));
-    jacobian_accumulate(p, p->huber_eval, p->d_J.p);
+    if ((rc = jacobian_accumulate(p, p->huber_eval, p->d_J.p))) return rc;
     std::vector<double> J(nj);
     CU(cudaMemcpyAsync(J.data(), p->d_J.p, nj * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
@@ -831,12 +832,13 @@ int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t 
 
 int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, double *b, double *cost) {
     if (!p || !z) return AAR_ERR_INVALID;
+    if (p->lm_active) { set_err("aar_reduced_system between aar_lm_begin and aar_lm_end would replace the resident iterate and LM state"); return AAR_ERR_INVALID; }
     CU(cudaSetDevice(p->device));
     int rc = upload_z(p, z, p->d_z.p); if (rc) return rc;
     if ((rc = zero_normal_equations(p))) return rc;
     CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
     residual(p, p->d_z.p, p->huber_eval, nullptr);
-    jacobian_accumulate(p, p->huber_eval, nullptr);
+    if ((rc = jacobian_accumulate(p, p->huber_eval, nullptr))) return rc;
     p->h_st->mu = mu; push_state(p);
     const int n_r = p->n_r;
     double *dS = p->d_red.p;
@@ -866,6 +868,7 @@ int aar_lm_begin(aar_problem *p, const double *z0, const aar_lm_params *params) 
         CU(cudaMemcpyAsync(p->d_z.p, p->d_z0.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     // MultiCamMapper::solve: hubberDelta = 10 before the solver starts (multicam_mapper.cpp:425)
     p->huber_cur = 10.f; p->huber_eval = 10.f;
+    CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
     // SparseLevMarq::init (sparselevmarq.h:237-249)
     CU(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
     residual(p, p->d_z.p, p->huber_cur, nullptr);
@@ -896,7 +899,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
         // ---- J, JtJ blocks, B (sparselevmarq.h:353-367)
         prof_mark(p, 0);
         if ((rc = zero_normal_equations(p))) return rc;
-        jacobian_accumulate(p, p->huber_eval, nullptr);
+        if ((rc = jacobian_accumulate(p, p->huber_eval, nullptr))) { p->lm_active = false; return rc; }
         prof_mark(p, 1);
         if (p->h_st->mu < 0) { // first iteration: mu = tau * max diag(JtJ) (sparselevmarq.h:369-377)
             p->h_st->maxdiag = -1e300; push_state(p);
@@ -953,6 +956,18 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
         CU(cudaMemcpyAsync(flags, p->d_flag.p, sizeof flags, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         if (!std::isfinite(p->h_st->trial_cost)) { set_err("non-finite cost at iteration %d", p->iter); p->lm_active = false; return AAR_ERR_NUMERIC; }
+        if (flags[0] || flags[2]) {
+            // flags[0]: a non-positive pivot in a frame block or in the reduced system (the kernels substituted 1 to keep going):
+            //   the step that was just taken is not the solution of the damped normal equations.  The reference does not check
+            //   its LDLT (sparselevmarq.h:394-400) and would continue on garbage; this path stops and says so.
+            // flags[2]: the rotation of a translation-perturbed inverse camera pose differed from the unperturbed one, so the
+            //   translation-only camera variants of k_expand_jac do not reproduce cv::Mat::inv() bit for bit.
+            set_err(flags[0] ? "non-positive Cholesky pivot at iteration %d (damped normal equations not positive definite)"
+                             : "camera inverse of a translation-perturbed pose changed its rotation at iteration %d (bit-exact table assumption violated)", p->iter);
+            CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
+            p->lm_active = false;
+            return AAR_ERR_NUMERIC;
+        }
         // ---- exit tests of SparseLevMarq::solve (sparselevmarq.h:458-464)
         const double currErr = p->cost, prevErr = p->prev_cost;
         if (!P.ignore_stop_rules) {
@@ -972,7 +987,6 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
         p->h_st->prev_cost = currErr; p->h_st->cost = currErr;
         if ((rc = push_state(p))) return rc;
         p->iter++; done_iters++;
-        (void)flags;
     }
     p->exit_code = mustExit;
     if (rep) { rep->final_cost = p->cost; rep->iterations = done_iters; rep->exit_code = mustExit; rep->total_tries = p->total_tries; }

@@ -983,7 +983,7 @@ int aar_oracle_lm_port(OracleHandle *h, double *z_io, int track, int max_trace, 
         if (std::fabs(prevErr - currErr) <= m.min_step_error_diff || std::fabs((prevErr - currErr) / rows) <= m.min_average_step_error_diff || !isStepAccepted) mustExit = 2;
         if (currErr > prevErr) mustExit = 3;
         if (trace && it < max_trace) { double *tr = trace + 6 * (size_t)it; tr[0] = currErr; tr[1] = mu; tr[2] = gain; tr[3] = ntries + (isStepAccepted ? 1 : 0); tr[4] = isStepAccepted; tr[5] = m.hubberDelta; }
-        m.optCallBack();
+        if (!track) m.optCallBack();   /* the callback is installed by solve() only (mcm.cpp:422); apps/track.cpp goes init -> track() */
         prevErr = currErr;
     }
     std::memcpy(z_io, curr_z.data(), (size_t)n * sizeof(double));
@@ -1056,7 +1056,7 @@ static int run_reference_slm(OracleHandle *h, double *z_io, int track, int max_t
         if (trace && it < max_trace) { double *tr = trace + 6 * (size_t)it; tr[0] = solver.currErr; tr[1] = solver.mu; tr[2] = 0; tr[3] = 0; tr[4] = (last_cost < 0 || solver.currErr < last_cost); tr[5] = m.hubberDelta; }
         last_cost = solver.currErr;
         it++;
-        m.optCallBack();
+        if (!track) m.optCallBack();   /* MultiCamMapper::track() never installs optCallBack (mcm.cpp:422 is in solve() only): hubberDelta stays 10 */
     });
     m.hubberDelta = 10;
     double fc = track ? solver.solve(z, f) : solver.solve(z, f, J);
