@@ -94,8 +94,8 @@ struct aar_problem {
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
-    DevBuf<int> d_batch_f; int nbatch = 0, win_slots = 0, win_frames = 0; bool acc_mma = false;   // k_jac_accumulate_mma: frame batches
-    DevBuf<int> d_perm_fm, d_perm_cm; bool acc_split = false, acc_staged = false, acc_staged_frames = false;                                       // k_acc_frames + k_acc_reduced: visiting orders
+    DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
+    bool legacy_acc = false;                                                          // AAR_ASM=legacy: round-1 lane-per-observation kernel (A/B aid)
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
@@ -107,7 +107,6 @@ struct aar_problem {
     DevBuf<float> d_Jn32; DevBuf<double> d_Jn64, d_Rv;
     int max_ms = 0, num_sms = 148; size_t smem_optin = 227 * 1024;
     bool use_cluster_solve = true;
-    cudaStream_t stream2 = nullptr; cudaEvent_t ev_slab[16] = {}; cudaEvent_t ev_join = nullptr; int jac_slabs = 1;
     int force_exact_staging = 0; long long exact_reruns = 0;
     DevProblem dp{};
     // ---- LM host mirror
@@ -164,94 +163,56 @@ int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_ou
 
 void prof_mark(aar_problem *p, int i) { if (p->profiling) cudaEventRecord(p->ev[i], p->stream); }
 
-// Launches the two Jacobian kernels.  With more than one slab the observations are cut into slabs and the two
-// kernels run on two streams, k_jac_accumulate of slab s next to k_jac_project of slab s+1 on the same SMs (one
-// 192-thread x 168-register CTA of the first and one 128-thread x 255-register CTA of the second fill the register file
-// of an SM together): the first is bound by FP64 issue, the second by the latency of its reduce / emit sequences, so
-// each could fill the other's bubbles.  MEASURED SLOWER on cfg 4 (profiles/r1_notes.md: 9.2 ms vs 6.35 ms per 5.1 M observations,
-// the projection kernel needs its 12 warps/SM), so the default is one slab; AAR_JAC_SLABS=n keeps the experiment reachable.
-template <typename JT, int AW>
-int launch_jacobian_t(aar_problem *p, float huber_eval, JT *Jn, int slabs) {
+// Launches the Jacobian kernels: k_jac_project (numerators + residual at z, one row per observation) and the tensor-core assembly
+// k_asm_pairs + k_asm_mruns (aar_assemble.cuh).  AAR_ASM=legacy selects the round-1 lane-per-observation kernel instead.
+template <typename JT>
+int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     const size_t tab_bytes = (size_t)((p->M * MK_TAB_S + 1) & ~1) * sizeof(double);
     const int tabs_smem = tab_bytes <= 48 * 1024;          // marker tables of the whole rig next to the per-warp pair buffers
     const size_t smem1 = (tabs_smem ? tab_bytes : 0) + PROJ_PAIR_SMEM_BYTES;
-    const bool mma = p->acc_mma && slabs == 1;
-    auto k1 = mma ? k_jac_project<JT, true> : k_jac_project<JT, false>; auto k2 = k_jac_accumulate<JT, AW>;
-    const size_t scr = (size_t)AW * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
-    // as many camera x marker pair accumulators as the shared memory left over by the fixed part (and, when the two
-    // kernels share an SM, by the projection kernel's tables) can hold
-    AccPlan pl; pl.s1 = 1.0 / (2 * p->J_delta); pl.s2 = pl.s1 * pl.s1;
-    { const char *e = getenv("AAR_ACC_SKIP"); pl.skip = e ? atoi(e) : 0; }
-    const size_t avail = p->smem_optin - 2048 - (slabs > 1 ? smem1 + 2048 : 0);
-    if (fix + scr > avail) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
-    pl.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, (avail - fix - scr) / 288);
-    const size_t smem2 = fix + (size_t)pl.hcm_smem * 288 + scr;
-    CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
-    CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const long long N = p->dp.N;
-    const long long per = slabs > 1 ? ((N + slabs - 1) / slabs + 31) / 32 * 32 : N;
-    cudaStream_t s2 = slabs > 1 ? p->stream2 : p->stream;
+    const double s1 = 1.0 / (2 * p->J_delta), s2 = s1 * s1;
+    const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
     prof_mark(p, 7);
-    int done = 0;
-    for (long long a = 0; a < N; a += per, done++) {
-        const long long b = std::min(N, a + per), n = b - a;
-        const int per_sm1 = slabs > 1 ? 1 : AAR_PROJ_MINBLOCKS;
-        const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm1 * p->num_sms, (n + PROJ_THREADS - 1) / PROJ_THREADS));
-        const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)p->num_sms, (n + AW * 32 - 1) / (AW * 32)));
-        k1<<<grid1, PROJ_THREADS, smem1, p->stream>>>(p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, a, b);
-        p->launches++;
-        if (slabs > 1) { CU(cudaEventRecord(p->ev_slab[done & 15], p->stream)); CU(cudaStreamWaitEvent(s2, p->ev_slab[done & 15], 0)); }
-        else prof_mark(p, 9);
-        if (mma && p->acc_split) {
-            // tensor-core accumulation split by key: every sum is visited in an order in which it has runs (aar_jacobian.cuh)
-            auto k4 = k_acc_frames<JT>; auto k5 = k_acc_reduced<JT>;
-            Acc2Plan q; q.s1 = pl.s1; q.s2 = pl.s2; q.nbatch = p->nbatch; q.win_slots = p->win_slots; q.win_frames = p->win_frames; q.hcm_smem = 0;
-            q.batch_f = p->d_batch_f.p; q.frame_obs_ptr = p->d_frame_obs_ptr.p;
-            Acc3Plan pm; pm.perm_fm = p->d_perm_fm.p; pm.perm_cm = p->d_perm_cm.p;
-            const size_t smem4 = ((size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
-            CU(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-            const int grid4 = std::max(1, std::min(p->num_sms, p->nbatch));
-            const size_t win_doubles = (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27, smem4s = ((win_doubles + 1) & ~(size_t)1) * sizeof(double) + accf_stage_bytes();
-            if (p->acc_staged_frames && sizeof(JT) == 4 && smem4s + 2048 <= p->smem_optin) {
-                CU(cudaFuncSetAttribute(k_acc_frames_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4s));
-                k_acc_frames_staged<<<grid4, ACC2_THREADS, smem4s, s2>>>(p->dp, q, pm, reinterpret_cast<const float *>(Jn), p->d_Rv.p, p->d_Hf.p, p->d_W.p);
-            } else
-                k4<<<grid4, ACC2_THREADS, smem4, s2>>>(p->dp, q, pm, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p);
-            p->launches++;
-            if (p->n_r > 0 && p->acc_staged) {
-                auto k6 = k_acc_reduced_staged<JT>;
-                CU(cudaFuncSetAttribute(k6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc3_smem_bytes<JT>()));
-                k6<<<2 * p->num_sms, ACC3_THREADS, acc3_smem_bytes<JT>(), s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
-            } else if (p->n_r > 0) k5<<<3 * p->num_sms, ACC3_THREADS, 0, s2>>>(p->dp, pm, pl.s1, pl.s2, Jn, p->d_Rv.p, p->d_Hrr.p, p->d_gr.p);
-            else p->launches--;
-        } else if (mma) {
-            // FP64 tensor-core accumulation: frame batches per CTA, frame-keyed blocks leave with plain stores (no zeroing pass needed)
-            auto k3 = k_jac_accumulate_mma<JT>;
-            Acc2Plan q; q.s1 = pl.s1; q.s2 = pl.s2; q.nbatch = p->nbatch; q.win_slots = p->win_slots; q.win_frames = p->win_frames;
-            q.batch_f = p->d_batch_f.p; q.frame_obs_ptr = p->d_frame_obs_ptr.p;
-            const size_t base3 = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
-            q.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, (p->smem_optin - 2048 - base3) / 288);
-            const size_t smem3 = base3 + (size_t)q.hcm_smem * 288;
-            CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            const int grid3 = std::max(1, std::min(p->num_sms, p->nbatch));
-            k3<<<grid3, ACC2_THREADS, smem3, s2>>>(p->dp, q, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
-        } else
-            k2<<<grid2, AW * 32, smem2, s2>>>(p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, a, b);
-        p->launches++;
+    if (p->legacy_acc) {
+        constexpr int AW = 8;
+        auto k1 = k_jac_project<JT, false>; auto k2 = k_jac_accumulate<JT, AW>;
+        const size_t scr = (size_t)AW * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
+        AccPlan pl; pl.s1 = s1; pl.s2 = s2; pl.skip = 0;
+        const size_t avail = p->smem_optin - 2048;
+        if (fix + scr > avail) { set_err("too many cameras + markers (%d) for the shared accumulators of k_jac_accumulate", p->nrc + p->nrm); return AAR_ERR_UNSUPPORTED; }
+        pl.hcm_smem = (int)std::min<size_t>((size_t)p->nrc * p->nrm, (avail - fix - scr) / 288);
+        const size_t smem2 = fix + (size_t)pl.hcm_smem * 288 + scr;
+        CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
+        CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)p->num_sms, (N + AW * 32 - 1) / (AW * 32)));
+        LAUNCH(p, k1, grid1, PROJ_THREADS, smem1, p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, 0LL, N);
+        prof_mark(p, 9);
+        LAUNCH(p, k2, grid2, AW * 32, smem2, p->dp, pl, Jn, p->d_Rv.p, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, 0LL, N);
+        prof_mark(p, 8);
+        return AAR_OK;
     }
-    if (slabs > 1) {
-        prof_mark(p, 9);                                   // end of the projection kernels on the main stream
-        CU(cudaEventRecord(p->ev_join, s2)); CU(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+    auto k1 = k_jac_project<JT, true>; auto k2 = k_asm_pairs<JT>; auto k3 = k_asm_mruns<JT>;
+    AsmPlan pl; pl.pair_info = p->d_pair_info.p; pl.mrun_info = p->d_mrun_info.p; pl.perm_fm = p->d_perm_fm.p; pl.npairs = p->npairs; pl.nmruns = p->nmruns;
+    pl.s1 = s1; pl.s2 = s2;
+    const size_t smem2 = (size_t)p->nrc * ACC_LD * sizeof(double), smem3 = (size_t)p->nrm * ACC_LD * sizeof(double);
+    pl.smem_acc = std::max(smem2, smem3) + 1024 <= p->smem_optin / AAR_ASM_MINBLOCKS;   // several CTAs per SM
+    CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
+    if (pl.smem_acc && smem2 > 48 * 1024) CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    if (pl.smem_acc && smem3 > 48 * 1024) CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    LAUNCH(p, k1, grid1, PROJ_THREADS, smem1, p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, 0LL, N);
+    prof_mark(p, 9);
+    const int per_sm = AAR_ASM_MINBLOCKS;
+    if (p->npairs > 0) {
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * p->num_sms, ((long long)p->npairs + ASM_WARPS - 1) / ASM_WARPS));
+        LAUNCH(p, k2, grid2, ASM_THREADS, pl.smem_acc ? smem2 : 0, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+    }
+    if (p->nmruns > 0) {
+        const int grid3 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * p->num_sms, ((long long)p->nmruns + ASM_WARPS - 1) / ASM_WARPS));
+        LAUNCH(p, k3, grid3, ASM_THREADS, pl.smem_acc ? smem3 : 0, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
     }
     prof_mark(p, 8);
     return AAR_OK;
-}
-template <typename JT>
-int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
-    int slabs = p->jac_slabs;
-    if (p->dp.N < 64LL * 1024 * slabs) slabs = 1;          // small problems: one launch each, nothing to overlap
-    if (slabs > 16) slabs = 16;
-    return slabs > 1 ? launch_jacobian_t<JT, 4>(p, huber_eval, Jn, slabs) : launch_jacobian_t<JT, 8>(p, huber_eval, Jn, 1);
 }
 
 // J^T J blocks and J^T r at d_z (sparselevmarq.h:353-367) into Hf / W / Hrr / gr; or the dense per-observation
@@ -266,17 +227,15 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
         const bool exact = p->force_exact_staging || attempt == 1;
         if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
         if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
-        const bool stores_frame_blocks = p->acc_mma && !(p->jac_slabs > 1 && p->dp.N >= 64LL * 1024 * p->jac_slabs);   // k_jac_accumulate_mma writes every Hf / W entry
-        if (!stores_frame_blocks) {
-            if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
-            if (p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
-        }
+        if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
+        // the tensor-core assembly stores every W block (each slot is owned by one run); the legacy kernel accumulates into them
+        if (p->legacy_acc && p->d_W.n) CU(cudaMemsetAsync(p->d_W.p, 0, p->d_W.n * sizeof(double), p->stream));
         if (N == 0) return AAR_OK;
         const size_t Np = (N + 31) / 32 * 32;      // whole tiles of 32 observations
-        if (p->d_Rv.n < 8 * Np) CU(p->d_Rv.alloc(8 * Np));
+        if (p->d_Rv.n < 8 * Np) CU(p->d_Rv.alloc(8 * Np));          // legacy: residuals [N/32][8][32]; assembly path: Huber weights [N][4]
         int rc;
-        if (exact) { if (p->d_Jn64.n < 144 * Np) CU(p->d_Jn64.alloc(144 * Np)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
-        else { if (p->d_Jn32.n < 144 * Np) CU(p->d_Jn32.alloc(144 * Np)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
+        if (exact) { if (p->d_Jn64.n < JROW * Np) CU(p->d_Jn64.alloc(JROW * Np)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
+        else { if (p->d_Jn32.n < JROW * Np) CU(p->d_Jn32.alloc(JROW * Np)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
         if (rc) return rc;
         if (exact) break;
         // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
@@ -496,10 +455,6 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     CU(cudaSetDevice(p->device));
     if (d->stream) p->stream = (cudaStream_t)d->stream; else { CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->own_stream = true; }
     for (auto &e : p->ev) CU(cudaEventCreate(&e));
-    CU(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
-    for (auto &e : p->ev_slab) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-    { const char *e = getenv("AAR_JAC_SLABS"); if (e && atoi(e) >= 1) p->jac_slabs = atoi(e); }
     CU(cudaMallocHost((void **)&p->h_st, sizeof(LmState)));
     CU(cudaMallocHost((void **)&p->h_red3, 8 * sizeof(double)));
     CU(cudaMallocHost((void **)&p->h_flags, 4 * sizeof(int)));
@@ -539,40 +494,43 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     UP(p->d_slot_frame, slot_frame); UP(p->d_frame_block_slot, frame_block_slot);
     {
         std::vector<int> fop((size_t)Fl + 1); for (int f = 0; f <= Fl; f++) fop[(size_t)f] = (int)(frame_ptr[(size_t)(p->f_begin + f)] - p->o_begin); UP(p->d_frame_obs_ptr, fop);
-        // frame batches of k_jac_accumulate_mma: consecutive frames, at most ACC2_OBS_CAP observations (a single frame may have
-        // more), ACC2_FRAME_CAP frames and slot_cap W slots — a CTA sums the frame-keyed blocks of a batch in shared memory
-        const int slot_cap = std::max(ACC2_SLOT_MIN, p->nrc + p->nrm);
-        std::vector<int> batch_f(1, 0);
-        int co = 0, cs = 0, cf = 0; p->win_slots = 1; p->win_frames = 1;
-        for (int f = 0; f < Fl; f++) {
-            const int no = fop[(size_t)f + 1] - fop[(size_t)f], ns = slot_ptr[(size_t)f + 1] - slot_ptr[(size_t)f];
-            if (cf > 0 && (co + no > ACC2_OBS_CAP || cs + ns > slot_cap || cf + 1 > ACC2_FRAME_CAP)) { batch_f.push_back(f); co = cs = cf = 0; }
-            co += no; cs += ns; cf++;
-            p->win_slots = std::max(p->win_slots, cs); p->win_frames = std::max(p->win_frames, cf);
+        // visiting orders of the tensor-core assembly (aar_assemble.cuh): the (frame, camera) pairs with their row ranges, and the
+        // rows of each frame by (marker, camera) cut into (frame, marker) runs.  Root-marker rows have no marker block: not listed.
+        std::vector<int4> pair_info((size_t)p->npairs);
+        for (long long o = 0; o < Nl; o++) {
+            const int pr = obs_pair[(size_t)o];
+            if (o == 0 || obs_pair[(size_t)o - 1] != pr) pair_info[(size_t)pr] = make_int4((int)o, 0, pair_fc[(size_t)pr].x, pair_fc[(size_t)pr].y);
+            pair_info[(size_t)pr].y++;
         }
-        batch_f.push_back(Fl);
-        p->nbatch = Fl > 0 ? (int)batch_f.size() - 1 : 0;
-        UP(p->d_batch_f, batch_f);
-        const size_t need = ((size_t)(p->nrc + p->nrm) * 27 + (size_t)p->win_slots * 36 + (size_t)p->win_frames * 27) * sizeof(double);
-        const char *e = getenv("AAR_ACC_MMA");
-        p->acc_mma = need + 2048 <= p->smem_optin && p->win_slots < 65535 && e && *e == '1';   // opt-in: measured on a par with k_jac_accumulate (profiles/r1_notes.md)
-        p->acc_split = need + 2048 <= p->smem_optin && e && (*e == '2' || *e == '3' || *e == '4');            // opt-in: k_acc_frames + k_acc_reduced
-        p->acc_staged = p->acc_split && (*e == '3' || *e == '4');                                // ... with k_acc_reduced_staged
-        p->acc_staged_frames = p->acc_split && *e == '4';                                         // ... and k_acc_frames_staged
-        if (p->acc_split) {
-            p->acc_mma = true;        // same row-major staging, same frame batches, Hf / W stored (not accumulated) by the kernel
-            // rows of each frame by (marker, camera); all rows by (camera, marker) — stable, so frames ascend inside a pair
-            std::vector<int> perm_fm((size_t)Nl), perm_cm((size_t)Nl);
-            for (long long o = 0; o < Nl; o++) perm_fm[(size_t)o] = (int)o;
-            auto key_mc = [&](int o) { return ((long long)((obs_cm[(size_t)o] >> 12) & 0x7ffff) << 12) | (obs_cm[(size_t)o] & 0xfff); };
-            for (int f = 0; f < Fl; f++)
-                std::stable_sort(perm_fm.begin() + fop[(size_t)f], perm_fm.begin() + fop[(size_t)f + 1], [&](int a, int b) { return key_mc(a) < key_mc(b); });
-            std::vector<long long> cnt((size_t)p->C * p->M + 1, 0);
-            for (long long o = 0; o < Nl; o++) cnt[(size_t)(obs_cm[(size_t)o] & 0xfff) * p->M + ((obs_cm[(size_t)o] >> 12) & 0x7ffff) + 1]++;
-            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-            for (long long o = 0; o < Nl; o++) perm_cm[(size_t)cnt[(size_t)(obs_cm[(size_t)o] & 0xfff) * p->M + ((obs_cm[(size_t)o] >> 12) & 0x7ffff)]++] = (int)o;
-            UP(p->d_perm_fm, perm_fm); UP(p->d_perm_cm, perm_cm);
+        UP(p->d_pair_info, pair_info);
+        std::vector<int> perm_fm; std::vector<int4> mrun_info;
+        if (p->opt_m) {
+            perm_fm.reserve((size_t)Nl); mrun_info.reserve((size_t)(ms_cum.empty() ? 0 : ms_cum.back()) + 16);
+            std::vector<int> cnt((size_t)p->M + 1);
+            for (int f = 0; f < Fl; f++) {
+                const int o0 = fop[(size_t)f], o1 = fop[(size_t)f + 1];
+                std::fill(cnt.begin(), cnt.end(), 0);
+                for (int o = o0; o < o1; o++) cnt[(size_t)((obs_cm[(size_t)o] >> 12) & 0x7ffff) + 1]++;
+                const int base = (int)perm_fm.size();
+                int run = 0;
+                for (int m = 0; m < p->M; m++) {            // counting sort by marker, stable: cameras ascend inside a run
+                    const int n = cnt[(size_t)m + 1];
+                    cnt[(size_t)m + 1] = (m == p->root_marker) ? -1 : base + run;
+                    if (n > 0 && m != p->root_marker) { mrun_info.push_back(make_int4(base + run, n, -1, m - (m > p->root_marker ? 1 : 0))); run += n; }
+                }
+                perm_fm.resize((size_t)base + run);
+                for (int o = o0; o < o1; o++) {
+                    const int m = (obs_cm[(size_t)o] >> 12) & 0x7ffff;
+                    if (m == p->root_marker) continue;
+                    perm_fm[(size_t)cnt[(size_t)m + 1]++] = o;
+                }
+            }
+            for (auto &r : mrun_info) r.z = slot_m[(size_t)perm_fm[(size_t)r.x]];
+            if ((long long)mrun_info.size() >= (1LL << 31) - 1) { set_err("too many (frame, marker) runs on one rank"); return AAR_ERR_UNSUPPORTED; }
         }
+        p->nmruns = (int)mrun_info.size();
+        UP(p->d_perm_fm, perm_fm); UP(p->d_mrun_info, mrun_info);
+        { const char *e = getenv("AAR_ASM"); p->legacy_acc = e && !strcmp(e, "legacy"); }
     }
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);
@@ -678,9 +636,6 @@ void aar_problem_destroy(aar_problem *p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : p->ev_slab) if (e) cudaEventDestroy(e);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
-    if (p->stream2) { cudaStreamSynchronize(p->stream2); cudaStreamDestroy(p->stream2); }
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_red3) cudaFreeHost(p->h_red3);
     if (p->h_flags) cudaFreeHost(p->h_flags);

@@ -128,7 +128,7 @@ __device__ __forceinline__ void load8(const float4 *a, const float4 *b, long lon
 } // namespace aar
 
 #include "aar_jacobian.cuh"
-#include "aar_accumulate_mma.cuh"
+#include "aar_assemble.cuh"
 
 namespace aar {
 

@@ -281,22 +281,33 @@ def test_exact_staging_fallback_matches(binding, oracle_mod, monkeypatch):
     assert np.abs(S32[iu] - S64[iu]).max() <= 1e-13 * np.abs(S64).max() and np.abs(b32 - b64).max() <= 1e-13 * np.abs(b64).max()
 
 
-def test_tensor_core_accumulation_matches_lane_per_observation_kernel(binding, oracle_mod, monkeypatch):
-    """k_jac_accumulate_mma (FP64 tensor cores, warp per observation, frame batches per CTA) and k_jac_accumulate (lane per
-    observation, transposed reductions) sum the same products in different orders: same normal equations to rounding, on a
-    rig with duplicates, an emptied frame, and root camera / marker observations."""
+def test_tensor_core_assembly_matches_oracle_and_legacy_kernel(binding, oracle_mod, monkeypatch):
+    """k_asm_pairs + k_asm_mruns (FP64 tensor cores, one warp per (frame, camera) pair / (frame, marker) run, aar_assemble.cuh)
+    against the oracle's normal equations and against the round-1 lane-per-observation kernel (AAR_ASM=legacy), which sums the
+    same products in another order: on a rig with duplicated detections, an emptied frame, root camera / marker observations,
+    with and without Huber weights, and for every Config flag combination."""
     rig = small_rig(seed=31, F=120)
     # duplicated (frame, cam, marker) detections (only the last one has Jacobian rows) and a frame that loses all its rows
     dup = np.array([5, 40, 41], np.int64)
     rig.det_frame = np.concatenate([rig.det_frame, rig.det_frame[dup]]); rig.det_cam = np.concatenate([rig.det_cam, rig.det_cam[dup]])
     rig.det_marker = np.concatenate([rig.det_marker, rig.det_marker[dup]]); rig.det_xy = np.concatenate([rig.det_xy, rig.det_xy[dup] + 0.5])
     rig.det_marker = rig.det_marker.copy(); rig.det_marker[rig.det_frame == rig.frame_ids[7]] = 99999
-    o = oracle_mod.Oracle(rig); z0 = o.mats2evec()
-    S0, b0, c0 = binding.Problem(rig).reduced_system(z0, 5.0)
-    S_o, b_o, _ = o.reduced_system(z0, 5.0)
-    iu = np.triu_indices(len(b0))
-    for mode in ("1", "2", "4"):                     # opt-in paths: k_jac_accumulate_mma; k_acc_frames + k_acc_reduced; the same, rows staged (profiles/r1_notes.md)
-        monkeypatch.setenv("AAR_ACC_MMA", mode)
-        S1, b1, c1 = binding.Problem(rig).reduced_system(z0, 5.0)
-        assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and abs(c1 - c0) <= 1e-13 * c0
-        assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max()
+    rig.det_xy = rig.det_xy.copy(); rig.det_xy[::29] += 9.0          # outliers, so that the Huber weights differ from 1
+    for huber in (False, True):
+        for cams, markers, objects in [(True, True, True), (False, True, True), (True, False, True), (True, True, False)]:
+            o = oracle_mod.Oracle(rig); o.set_config(cams=cams, markers=markers, objects=objects, with_huber=huber, huber_delta=2.5)
+            z0 = o.mats2evec()
+            kw = dict(cams=cams, markers=markers, objects=objects, with_huber=huber)
+            monkeypatch.delenv("AAR_ASM", raising=False)
+            S1, b1, c1 = binding.Problem(rig, **kw).reduced_system(z0, 5.0)
+            monkeypatch.setenv("AAR_ASM", "legacy")
+            S0, b0, c0 = binding.Problem(rig, **kw).reduced_system(z0, 5.0)
+            monkeypatch.delenv("AAR_ASM", raising=False)
+            iu = np.triu_indices(len(b0))
+            if len(b0):
+                assert np.abs(S1[iu] - S0[iu]).max() <= 1e-12 * np.abs(S0).max() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max(), (huber, cams, markers, objects)
+            assert abs(c1 - c0) <= 1e-13 * c0
+            if cams and markers and objects:          # the oracle's reduced_system hook is written for the full Config
+                S_o, b_o, _ = o.reduced_system(z0, 5.0)
+                if len(b0):
+                    assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max(), (huber, cams, markers, objects)
