@@ -29,9 +29,10 @@ namespace aar {
 
 struct AsmPlan {
     const int4 *pair_info;      // [npairs]  first row, rows, local frame, camera
+    const int *pair_slot;       // [npairs]  W slot of the pair's (frame, camera) block, -1: none
     const int4 *mrun_info;      // [nmruns]  first entry of perm_fm, entries, W slot (-1: none), reduced marker block
-    const int *perm_fm;         // [N]       rows of each frame by (marker, camera); root-marker rows are not listed
-    int npairs, nmruns;
+    const int *perm_fm;         // [nperm]   rows of each frame by (marker, camera); root-marker rows are not listed
+    int npairs, nmruns, nperm;
     int smem_acc;               // 1: Hcc / Hmm accumulators in shared memory; 0: straight to global (rigs too large for 227 KB)
     double s1, s2;              // 1 / (2 delta), 1 / (2 delta)^2: the numerators are divided here, once per sum
 };
@@ -45,9 +46,33 @@ template <> struct Vec2<double> { typedef double2 type; };
 
 constexpr int ASM_THREADS = 256, ASM_WARPS = ASM_THREADS / 32;
 constexpr int ACC_LD = 28;      // 27 values of a packed symmetric block + gradient, padded to an even stride
+// Rows reach the warps through per-warp rings of shared-memory stages filled by the bulk-copy engine (cp.async.bulk + mbarrier
+// complete_tx): ASM_NST stages of ASM_SROWS rows are in flight per warp at no cost in registers or issue slots.  ncu of the
+// version that loaded fragments straight from global memory (one row in flight per warp): 8.4 cycles of long-scoreboard stall
+// per issued instruction, 40 % of the DRAM bandwidth; a register ring of four rows was slower still (profiles/r2_notes.md).
+constexpr int ASM_NST = 4, ASM_SROWS = 4;
+constexpr int ASM_MROW = 112;   // elements of a staged row the marker pass needs: [Jm (48) | Jf (48) | e (8) | marker index, pad (8)]
 #ifndef AAR_ASM_MINBLOCKS
-#define AAR_ASM_MINBLOCKS 3
+#define AAR_ASM_MINBLOCKS 2
 #endif
+template <typename JT> __host__ __device__ constexpr int asm_stage_bytes(int row_elems) { return ASM_SROWS * (row_elems * (int)sizeof(JT) + 32); }   // rows | Huber weights (4 doubles per row)
+template <typename JT> __host__ __device__ constexpr size_t asm_ring_bytes(int row_elems) { return (size_t)ASM_WARPS * ASM_NST * asm_stage_bytes<JT>(row_elems); }
+__host__ __device__ inline size_t asm_acc_bytes(int nblk) { return ((size_t)nblk * ACC_LD * sizeof(double) + 127) & ~(size_t)127; }
+constexpr size_t ASM_BAR_BYTES = 256;   // ASM_WARPS x ASM_NST mbarriers
+
+// ---- mbarrier / bulk copy (PTX ISA: mbarrier, cp.async.bulk)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 // index of fragment element (row g, column j) in a packed block [upper triangle by rows (21) | gradient (6)], or -1
 __device__ __forceinline__ int packed27(int g, int j) {
@@ -72,191 +97,233 @@ __device__ __forceinline__ void flush_diag_blocks(const double *__restrict__ acc
         } else atomicAdd(gr + d0 + (e - 21), v * s1);
     }
 }
+// a diagonal block's fragment straight to global memory (rigs whose accumulators do not fit shared memory)
+__device__ __forceinline__ void red_diag_block(const double (&T)[2], int g, int q, int d0, int n_r, double s1, double s2, bool with_grad, double *__restrict__ Hrr, double *__restrict__ gr) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const int j = 2 * q + e; const double v = T[e];
+        if (g >= 6) continue;
+        if (j == 6) { if (with_grad) atomicAdd(gr + d0 + g, v * s1); }
+        else if (j < 6 && j >= g) { atomicAdd(Hrr + (size_t)(d0 + g) * n_r + d0 + j, v * s2); if (j != g) atomicAdd(Hrr + (size_t)(d0 + j) * n_r + d0 + g, v * s2); }
+    }
+}
+
+// first index i in [0, n) with info[i].x >= key (info[].x ascending): where a warp's share of the row stream starts
+__device__ __forceinline__ int lower_bound_x(const int4 *__restrict__ info, int n, long long key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)info[mid].x < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 
 // One lane's share of one staged row (JROW elements per observation, aar_jacobian.cuh): element pair (2q, 2q + 1) of fragment
-// row g of each group, three 8-byte (float staging) loads through three per-lane pointers:
+// row g of each group, 8-byte (float staging) shared-memory loads at three per-lane offsets:
 //   frame group   elements 96 + 8 g + 2q of [Jf (48) | e (8) | marker index, pad (8)] for every g: row 6 is the residual
 //   marker group  48 + 8 g + 2q for g < 6; the residual (144 + 2q) for g == 6, so that the fragment is [Jm | r] as it stands
 //   camera group  8 g + 2q for g < 6
 // Whatever the lanes of fragment rows 6 / 7 hold beyond that only reaches rows / columns 6 and 7 of a product (element (i, j) of
 // A^T B is the dot product of fragment row i of A with fragment row j of B), which are never read, except column 6 of a product
-// with [X | r] — so nothing is masked.
-template <typename JT> struct RowFrag { typename Vec2<JT>::type c, m, f; };
-template <typename JT> struct LanePtrs {
-    const JT *c, *m, *f;
-    __device__ __forceinline__ LanePtrs(const JT *Jn, int g, int q) {
-        c = Jn + (g < 6 ? 8 * g + 2 * q : 144 + 2 * q);
-        m = Jn + (g < 6 ? 48 + 8 * g + 2 * q : 144 + 2 * q);
-        f = Jn + 96 + 8 * g + 2 * q;
-    }
-};
-template <typename JT, bool WITH_C, bool WITH_M, bool WITH_F>
-__device__ __forceinline__ void load_frag(const LanePtrs<JT> &lp, int o, RowFrag<JT> &x) {
-    typedef typename Vec2<JT>::type V2;
-    const size_t off = (size_t)o * JROW;
-    if (WITH_C) x.c = *reinterpret_cast<const V2 *>(lp.c + off);
-    if (WITH_M) x.m = *reinterpret_cast<const V2 *>(lp.m + off);
-    if (WITH_F) x.f = *reinterpret_cast<const V2 *>(lp.f + off);
-}
-// the marker index of the row, stored as an integer in element 152 (fragment row 7, q = 0): broadcast from lane 28
-template <typename JT> __device__ __forceinline__ int frag_marker(const RowFrag<JT> &x);
-template <> __device__ __forceinline__ int frag_marker<float>(const RowFrag<float> &x) { return __shfl_sync(0xffffffffu, __float_as_int(x.f.x), 28); }
-template <> __device__ __forceinline__ int frag_marker<double>(const RowFrag<double> &x) { return __shfl_sync(0xffffffffu, __double2loint(x.f.x), 28); }
+// with [X | r] — so nothing is masked.  Half-warps read 128 consecutive bytes (or a broadcast): no bank conflicts.
 
 // ------------------------------------------------------------------------------------------------
-// Row order: one warp per (frame, camera) pair.
+// Row order: run = the rows of one (frame, camera) pair.  Every warp owns a contiguous share of the row stream (cut at pair
+// boundaries, balanced by rows), so its ring never drains and the Hff / gf sums of a frame leave once per frame, not per pair.
 template <typename JT>
 __global__ void __launch_bounds__(ASM_THREADS, AAR_ASM_MINBLOCKS) k_asm_pairs(DevProblem p, AsmPlan pl, const JT *__restrict__ Jn /* [N][JROW] */, const double *__restrict__ Hw /* [N][4] Huber weights or null */,
                                                                              double *__restrict__ Hf, double *__restrict__ W, double *__restrict__ Hrr, double *__restrict__ gr) {
-    extern __shared__ __align__(16) double sAcc[];                 // [nrc][ACC_LD]
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    const bool opt_c = p.opt_c != 0, opt_m = p.opt_m != 0, opt_f = p.opt_f != 0;
-    double *accC = pl.smem_acc ? sAcc : nullptr;
-    if (accC) { for (int i = tid; i < p.nrc * ACC_LD; i += ASM_THREADS) sAcc[i] = 0.0; __syncthreads(); }
-    const int n_r = p.n_r, nrm1 = max(p.nrm - 1, 0);
+    typedef typename Vec2<JT>::type V2;
+    constexpr int ROWB = JROW * (int)sizeof(JT), STAGE = asm_stage_bytes<JT>(JROW);
+    extern __shared__ __align__(128) unsigned char asm_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    const bool opt_c = p.opt_c != 0, opt_f = p.opt_f != 0, with_cm = opt_c && p.opt_m != 0;
+    const size_t acc_bytes = pl.smem_acc ? asm_acc_bytes(p.nrc) : 0;
+    double *accC = pl.smem_acc ? reinterpret_cast<double *>(asm_smem) : nullptr;
+    unsigned char *ring = asm_smem + acc_bytes + ASM_BAR_BYTES + (size_t)warp * ASM_NST * STAGE;
+    const unsigned bar0 = smem_u32(asm_smem + acc_bytes) + warp * ASM_NST * 8, ring0 = smem_u32(ring);
+    if (accC) for (int i = tid; i < p.nrc * ACC_LD; i += ASM_THREADS) accC[i] = 0.0;
+    if (lane < ASM_NST) mbar_init(bar0 + 8 * lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int n_r = p.n_r, nrm1 = max(p.nrm - 1, 0), nrc1 = max(p.nrc - 1, 0);
     const double s1 = pl.s1, s2 = pl.s2;
     // this lane's two result elements (row g, columns 2q and 2q + 1)
     const int j0 = 2 * q, j1 = 2 * q + 1;
     const int i27_0 = packed27(g, j0), i27_1 = packed27(g, j1);
-    const bool in36 = g < 6 && j1 < 6;
-    const bool row_lt6 = g < 6, row_is6 = g == 6;
-    const LanePtrs<JT> lp(Jn, g, q);
-    const long long gw = (long long)blockIdx.x * ASM_WARPS + (tid >> 5), nw = (long long)gridDim.x * ASM_WARPS;
-    for (long long pr = gw; pr < pl.npairs; pr += nw) {
-        const int4 pi = pl.pair_info[pr];
-        const int o0 = pi.x, n = pi.y, f = pi.z, c = pi.w;
-        const bool act_c = opt_c && c != p.root_cam, act_cm = act_c && opt_m;
-        const int cb = c - (c > p.root_cam ? 1 : 0);
-        if (pr + nw < pl.npairs) {        // the next pair of this warp towards L2: its rows are consecutive
-            const int4 pn = pl.pair_info[pr + nw];
-            const char *nx = reinterpret_cast<const char *>(Jn + (size_t)pn.x * JROW);
-            const int bytes = pn.y * JROW * (int)sizeof(JT);
-            for (int b = lane * 128; b < bytes; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + b));
-        }
-        double Tff[2] = {0, 0}, Tcf[2] = {0, 0}, Tcc[2] = {0, 0};
+    const bool in36 = g < 6 && j1 < 6, row_lt6 = g < 6, row_is6 = g == 6;
+    const int off_c = (g < 6 ? 8 * g + 2 * q : 144 + 2 * q) * (int)sizeof(JT), off_m = (g < 6 ? 48 + 8 * g + 2 * q : 144 + 2 * q) * (int)sizeof(JT), off_f = (96 + 8 * g + 2 * q) * (int)sizeof(JT);
+    // this warp's share: pairs [pA, pB), rows [R0, R1)
+    const long long gw = (long long)blockIdx.x * ASM_WARPS + warp, nw = (long long)gridDim.x * ASM_WARPS;
+    const int pA = lower_bound_x(pl.pair_info, pl.npairs, (long long)p.N * gw / nw), pB = lower_bound_x(pl.pair_info, pl.npairs, (long long)p.N * (gw + 1) / nw);
+    if (pA < pB) {
+        const int R0 = pl.pair_info[pA].x, R1 = pB < pl.npairs ? pl.pair_info[pB].x : (int)p.N;
+        const int nst = (R1 - R0 + ASM_SROWS - 1) / ASM_SROWS;
+        auto issue = [&](int k) {            // stage k of the stream into slot k % ASM_NST
+            if (lane == 0) {
+                const int r = R0 + k * ASM_SROWS, nr = min(ASM_SROWS, R1 - r), slot = k % ASM_NST;
+                const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
+                mbar_expect_tx(bar, nr * (ROWB + (Hw ? 32 : 0)));
+                bulk_g2s(dst, Jn + (size_t)r * JROW, nr * ROWB, bar);
+                if (Hw) bulk_g2s(dst + ASM_SROWS * ROWB, Hw + (size_t)r * 4, nr * 32, bar);
+            }
+        };
+        for (int k = 0; k < min(ASM_NST, nst); k++) issue(k);
+        // run descriptors: lane j holds pair pbase + j
+        int pbase = pA;
+        int4 mine = pl.pair_info[min(pbase + lane, pB - 1)];
+        int mslot = pl.pair_slot[min(pbase + lane, pB - 1)];
+        int jp = 0, left = __shfl_sync(0xffffffffu, mine.y, 0), cam = __shfl_sync(0xffffffffu, mine.w, 0), frame = __shfl_sync(0xffffffffu, mine.z, 0);
+        bool act_c = opt_c && cam != p.root_cam;
+        int cb = min(cam - (cam > p.root_cam ? 1 : 0), nrc1);
         double *hcm_row = Hrr + (size_t)(6 * cb + min(g, 5)) * n_r + 6 * p.nrc + j0;      // this lane's element of marker block 0 in the camera's block row
-        RowFrag<JT> xa, xb;
-        xa.c.x = xa.c.y = xa.m.x = xa.m.y = xb.c.x = xb.c.y = xb.m.x = xb.m.y = (JT)0;
-        auto load = [&](int o, RowFrag<JT> &x) {
-            if (act_cm) load_frag<JT, true, true, true>(lp, o, x); else if (act_c) load_frag<JT, true, false, true>(lp, o, x); else load_frag<JT, false, false, true>(lp, o, x);
-        };
-        auto step = [&](int t, RowFrag<JT> &x, RowFrag<JT> &nx) {
-            if (t + 1 < n) load(o0 + t + 1, nx);                                 // the next row in flight during this one
-            double f0 = (double)x.f.x, f1 = (double)x.f.y;                       // [Jf | r]: rows 0..5 Jf, row 6 the residual
-            if (Hw && row_is6) { const double w = Hw[(size_t)(o0 + t) * 4 + q]; f0 = w * f0; f1 = w * f1; }   // Huber: r = w * e (mcm.cpp:1014-1019)
-            dmma884(Tff, f0, f0); dmma884(Tff, f1, f1);                         // Hff and, in column 6, gf
-            if (act_c) {
-                const double c0 = (double)x.c.x, c1 = (double)x.c.y;
-                dmma884(Tcf, c0, f0); dmma884(Tcf, c1, f1);                     // W_c and, in column 6, gc
-                dmma884(Tcc, c0, c0); dmma884(Tcc, c1, c1);
-                if (act_cm) {
-                    // camera x marker block of this observation: no other observation of the frame shares it.  A root-marker
-                    // row has zero marker columns: zeros are added to a valid block.
-                    double Tcm[2] = {0, 0};
-                    dmma884(Tcm, c0, (double)x.m.x); dmma884(Tcm, c1, (double)x.m.y);
-                    const int mk = frag_marker<JT>(x);
-                    const int mb = min(mk - (mk > p.root_marker ? 1 : 0), nrm1);
-                    if (in36) { double *dst = hcm_row + 6 * mb; atomicAdd(dst, Tcm[0] * s2); atomicAdd(dst + 1, Tcm[1] * s2); }
+        double Tff[2] = {0, 0}, Tcf[2] = {0, 0}, Tcc[2] = {0, 0};
+        for (int k = 0; k < nst; k++) {
+            const int slot = k % ASM_NST, nr = min(ASM_SROWS, R1 - (R0 + k * ASM_SROWS));
+            mbar_wait(bar0 + 8 * slot, (k / ASM_NST) & 1);
+            const unsigned char *sb = ring + slot * STAGE;
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                const unsigned char *row = sb + r * ROWB;
+                const V2 xf = *reinterpret_cast<const V2 *>(row + off_f);
+                double f0 = (double)xf.x, f1 = (double)xf.y;                   // [Jf | r]: rows 0..5 Jf, row 6 the residual
+                if (Hw && row_is6) { const double w = reinterpret_cast<const double *>(sb + ASM_SROWS * ROWB)[r * 4 + q]; f0 = w * f0; f1 = w * f1; }   // Huber: r = w * e (mcm.cpp:1014-1019)
+                dmma884(Tff, f0, f0); dmma884(Tff, f1, f1);                     // Hff and, in column 6, gf
+                if (opt_c) {            // a root-camera row has zero camera columns: its products are zeros that nobody stores
+                    const V2 xc = *reinterpret_cast<const V2 *>(row + off_c);
+                    const double c0 = (double)xc.x, c1 = (double)xc.y;
+                    dmma884(Tcf, c0, f0); dmma884(Tcf, c1, f1);                 // W_c and, in column 6, gc
+                    dmma884(Tcc, c0, c0); dmma884(Tcc, c1, c1);
+                    if (with_cm) {
+                        // camera x marker block of this observation: no other observation of the frame shares it.  A root-marker
+                        // row has zero marker columns: zeros are added to a valid block.
+                        const V2 xm = *reinterpret_cast<const V2 *>(row + off_m);
+                        double Tcm[2] = {0, 0};
+                        dmma884(Tcm, c0, (double)xm.x); dmma884(Tcm, c1, (double)xm.y);
+                        const int mk = *reinterpret_cast<const int *>(row + 152 * (int)sizeof(JT));
+                        const int mb = min(mk - (mk > p.root_marker ? 1 : 0), nrm1);
+                        if (in36 && act_c) { double *dst = hcm_row + 6 * mb; atomicAdd(dst, Tcm[0] * s2); atomicAdd(dst + 1, Tcm[1] * s2); }
+                    }
+                }
+                if (--left == 0) {
+                    // ---- the pair's sums
+                    if (act_c) {
+                        const int slot_c = __shfl_sync(0xffffffffu, mslot, jp);
+                        if (opt_f && in36 && slot_c >= 0)      // W_c: this pair owns the slot
+                            *reinterpret_cast<double2 *>(W + (size_t)slot_c * 36 + g * 6 + j0) = make_double2(Tcf[0] * s2, Tcf[1] * s2);
+                        // gc (column 6 of Jc^T [Jf | r]) and the upper triangle of Hcc
+                        if (accC) {
+                            double *dst = accC + cb * ACC_LD;
+                            if (row_lt6 && j0 == 6) atomicAdd(dst + 21 + g, Tcf[0]);
+                            if (i27_0 >= 0 && j0 < 6) atomicAdd(dst + i27_0, Tcc[0]);
+                            if (i27_1 >= 0 && j1 < 6) atomicAdd(dst + i27_1, Tcc[1]);
+                        } else {
+                            if (row_lt6 && j0 == 6) atomicAdd(gr + 6 * cb + g, Tcf[0] * s1);
+                            red_diag_block(Tcc, g, q, 6 * cb, n_r, s1, s2, false, Hrr, gr);
+                        }
+                    }
+                    Tcf[0] = Tcf[1] = Tcc[0] = Tcc[1] = 0.0;
+                    // next pair of the stream
+                    int nframe = -1;
+                    if (++jp == 32 && pbase + 32 < pB) { pbase += 32; jp = 0; mine = pl.pair_info[min(pbase + lane, pB - 1)]; mslot = pl.pair_slot[min(pbase + lane, pB - 1)]; }
+                    if (pbase + jp < pB) {
+                        left = __shfl_sync(0xffffffffu, mine.y, jp); cam = __shfl_sync(0xffffffffu, mine.w, jp); nframe = __shfl_sync(0xffffffffu, mine.z, jp);
+                        act_c = opt_c && cam != p.root_cam; cb = min(cam - (cam > p.root_cam ? 1 : 0), nrc1);
+                        hcm_row = Hrr + (size_t)(6 * cb + min(g, 5)) * n_r + 6 * p.nrc + j0;
+                    }
+                    if (nframe != frame) {      // Hff + gf: the warp's pairs of this frame are done (other warps may add their share)
+                        if (opt_f) {
+                            double *dst = Hf + (size_t)frame * HF_STRIDE;
+                            if (i27_0 >= 0) atomicAdd(dst + i27_0, Tff[0] * (j0 == 6 ? s1 : s2));
+                            if (i27_1 >= 0) atomicAdd(dst + i27_1, Tff[1] * s2);
+                        }
+                        Tff[0] = Tff[1] = 0.0; frame = nframe;
+                    }
                 }
             }
-        };
-        load(o0, xa);
-        for (int t = 0; t < n; t += 2) {
-            step(t, xa, xb);
-            if (t + 1 < n) step(t + 1, xb, xa);
-        }
-        // ---- the pair's sums
-        if (opt_f) {        // Hff + gf: every pair of the frame adds its share
-            double *dst = Hf + (size_t)f * HF_STRIDE;
-            if (i27_0 >= 0) atomicAdd(dst + i27_0, Tff[0] * (j0 == 6 ? s1 : s2));
-            if (i27_1 >= 0) atomicAdd(dst + i27_1, Tff[1] * s2);
-        }
-        if (act_c) {
-            if (opt_f && in36)      // W_c: this pair owns the slot
-                *reinterpret_cast<double2 *>(W + (size_t)p.obs_slot_c[o0] * 36 + g * 6 + j0) = make_double2(Tcf[0] * s2, Tcf[1] * s2);
-            // gc (column 6 of Jc^T [Jf | r]) and the upper triangle of Hcc
-            if (accC) {
-                double *dst = accC + cb * ACC_LD;
-                if (row_lt6 && j0 == 6) atomicAdd(dst + 21 + g, Tcf[0]);
-                if (i27_0 >= 0 && j0 < 6) atomicAdd(dst + i27_0, Tcc[0]);
-                if (i27_1 >= 0 && j1 < 6) atomicAdd(dst + i27_1, Tcc[1]);
-            } else {
-                const int d0 = 6 * cb;
-                if (row_lt6 && j0 == 6) atomicAdd(gr + d0 + g, Tcf[0] * s1);
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int j = 2 * q + e; const double v = e ? Tcc[1] : Tcc[0];
-                    if (row_lt6 && j < 6 && j >= g) { atomicAdd(Hrr + (size_t)(d0 + g) * n_r + d0 + j, v * s2); if (j != g) atomicAdd(Hrr + (size_t)(d0 + j) * n_r + d0 + g, v * s2); }
-                }
-            }
+            __syncwarp();                     // every lane is done reading the slot
+            if (k + ASM_NST < nst) issue(k + ASM_NST);
         }
     }
     if (accC) { __syncthreads(); flush_diag_blocks(accC, p.nrc, 0, n_r, s1, s2, Hrr, gr); }
 }
 
 // ------------------------------------------------------------------------------------------------
-// (marker, camera) order inside each frame: one warp per (frame, marker) run.
+// (marker, camera) order inside each frame: run = the rows of one (frame, marker), gathered through perm_fm — one bulk copy of
+// the row's [Jm | Jf | e | marker] part (and one of its Huber weights) per row.
 template <typename JT>
 __global__ void __launch_bounds__(ASM_THREADS, AAR_ASM_MINBLOCKS) k_asm_mruns(DevProblem p, AsmPlan pl, const JT *__restrict__ Jn, const double *__restrict__ Hw,
                                                                              double *__restrict__ W, double *__restrict__ Hrr, double *__restrict__ gr) {
-    extern __shared__ __align__(16) double sAcc[];                 // [nrm][ACC_LD]
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    typedef typename Vec2<JT>::type V2;
+    constexpr int ROWB = ASM_MROW * (int)sizeof(JT), STAGE = asm_stage_bytes<JT>(ASM_MROW);
+    extern __shared__ __align__(128) unsigned char asm_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const bool opt_f = p.opt_f != 0;
-    double *accM = pl.smem_acc ? sAcc : nullptr;
-    if (accM) { for (int i = tid; i < p.nrm * ACC_LD; i += ASM_THREADS) sAcc[i] = 0.0; __syncthreads(); }
+    const size_t acc_bytes = pl.smem_acc ? asm_acc_bytes(p.nrm) : 0;
+    double *accM = pl.smem_acc ? reinterpret_cast<double *>(asm_smem) : nullptr;
+    unsigned char *ring = asm_smem + acc_bytes + ASM_BAR_BYTES + (size_t)warp * ASM_NST * STAGE;
+    const unsigned bar0 = smem_u32(asm_smem + acc_bytes) + warp * ASM_NST * 8, ring0 = smem_u32(ring);
+    if (accM) for (int i = tid; i < p.nrm * ACC_LD; i += ASM_THREADS) accM[i] = 0.0;
+    if (lane < ASM_NST) mbar_init(bar0 + 8 * lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
     const int n_r = p.n_r;
     const double s1 = pl.s1, s2 = pl.s2;
     const int j0 = 2 * q, j1 = 2 * q + 1;
     const int i27_0 = packed27(g, j0), i27_1 = packed27(g, j1);
-    const bool in36 = g < 6 && j1 < 6, row_lt6 = g < 6, row_is6 = g == 6;
-    const LanePtrs<JT> lp(Jn, g, q);
-    const long long gw = (long long)blockIdx.x * ASM_WARPS + (tid >> 5), nw = (long long)gridDim.x * ASM_WARPS;
-    // run descriptors and row indices are fetched one run ahead, and the rows of the next run pulled towards L2
-    int4 ri = gw < pl.nmruns ? pl.mrun_info[gw] : make_int4(0, 0, -1, 0);
-    int my = lane < ri.y ? pl.perm_fm[ri.x + lane] : 0;
-    for (long long r = gw; r < pl.nmruns; r += nw) {
-        const int i0 = ri.x, n = ri.y, slot = ri.z, mb = ri.w, my_cur = my;
-        if (r + nw < pl.nmruns) {
-            ri = pl.mrun_info[r + nw];
-            my = lane < ri.y ? pl.perm_fm[ri.x + lane] : 0;
-            if (lane < ri.y) {
-                const char *nx = reinterpret_cast<const char *>(Jn + (size_t)my * JROW + 48);      // marker + frame groups: 112 elements
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx)); asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128 * sizeof(JT) / 4));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 256 * sizeof(JT) / 4)); asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 112 * sizeof(JT) - 1));
+    const bool in36 = g < 6 && j1 < 6, row_is6 = g == 6;
+    const int off_m = (g < 6 ? 8 * g + 2 * q : 96 + 2 * q) * (int)sizeof(JT), off_f = (48 + 8 * g + 2 * q) * (int)sizeof(JT);      // relative to element 48 of the row
+    // this warp's share: runs [rA, rB), entries [E0, E1) of perm_fm
+    const long long gw = (long long)blockIdx.x * ASM_WARPS + warp, nw = (long long)gridDim.x * ASM_WARPS;
+    const int rA = lower_bound_x(pl.mrun_info, pl.nmruns, (long long)pl.nperm * gw / nw), rB = lower_bound_x(pl.mrun_info, pl.nmruns, (long long)pl.nperm * (gw + 1) / nw);
+    if (rA < rB) {
+        const int E0 = pl.mrun_info[rA].x, E1 = rB < pl.nmruns ? pl.mrun_info[rB].x : pl.nperm;
+        const int nst = (E1 - E0 + ASM_SROWS - 1) / ASM_SROWS;
+        // row indices of the producer: lane l holds entry E0 + 32 * pblk + l, the next block is already on its way
+        int pblk = 0;
+        int pv = E0 + lane < E1 ? pl.perm_fm[E0 + lane] : 0, pvn = E0 + 32 + lane < E1 ? pl.perm_fm[E0 + 32 + lane] : 0;
+        auto issue = [&](int k) {            // stage k of the stream into slot k % ASM_NST: one copy per row, issued by lanes 0 .. nr - 1
+            const int e = k * ASM_SROWS, nr = min(ASM_SROWS, E1 - E0 - e), slot = k % ASM_NST;      // a stage never straddles a block of 32 entries
+            if ((e >> 5) != pblk) { pblk++; pv = pvn; const int nx = E0 + 32 * (pblk + 1) + lane; pvn = nx < E1 ? pl.perm_fm[nx] : 0; }
+            const int o = __shfl_sync(0xffffffffu, pv, (e & 31) + (lane & (ASM_SROWS - 1)));
+            const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
+            if (lane == 0) mbar_expect_tx(bar, nr * (ROWB + (Hw ? 32 : 0)));
+            __syncwarp();
+            if (lane < nr) {
+                bulk_g2s(dst + lane * ROWB, Jn + (size_t)o * JROW + 48, ROWB, bar);
+                if (Hw) bulk_g2s(dst + ASM_SROWS * ROWB + lane * 32, Hw + (size_t)o * 4, 32, bar);
             }
-        }
-        double Tmm[2] = {0, 0}, Tmf[2] = {0, 0};
-        RowFrag<JT> xa, xb;
-        xa.f.x = xa.f.y = xb.f.x = xb.f.y = (JT)0;
-        auto row_of = [&](int t) { return t < 32 ? __shfl_sync(0xffffffffu, my_cur, t & 31) : pl.perm_fm[i0 + t]; };
-        int o_cur = row_of(0);
-        if (opt_f) load_frag<JT, false, true, true>(lp, o_cur, xa); else load_frag<JT, false, true, false>(lp, o_cur, xa);
-        auto step = [&](int t, RowFrag<JT> &x, RowFrag<JT> &nx) {
-            const int o_this = o_cur;
-            if (t + 1 < n) { o_cur = row_of(t + 1); if (opt_f) load_frag<JT, false, true, true>(lp, o_cur, nx); else load_frag<JT, false, true, false>(lp, o_cur, nx); }
-            double m0 = (double)x.m.x, m1 = (double)x.m.y;                       // [Jm | r]
-            if (Hw && row_is6) { const double w = Hw[(size_t)o_this * 4 + q]; m0 = w * m0; m1 = w * m1; }
-            dmma884(Tmm, m0, m0); dmma884(Tmm, m1, m1);                         // Hmm and, in column 6, gm
-            if (opt_f) { dmma884(Tmf, m0, (double)x.f.x); dmma884(Tmf, m1, (double)x.f.y); }      // W_m
         };
-        for (int t = 0; t < n; t += 2) {
-            step(t, xa, xb);
-            if (t + 1 < n) step(t + 1, xb, xa);
-        }
-        if (opt_f && slot >= 0 && in36)         // W_m: this run owns the slot
-            *reinterpret_cast<double2 *>(W + (size_t)slot * 36 + g * 6 + j0) = make_double2(Tmf[0] * s2, Tmf[1] * s2);
-        if (accM) {
-            double *dst = accM + mb * ACC_LD;
-            if (i27_0 >= 0) atomicAdd(dst + i27_0, Tmm[0]);
-            if (i27_1 >= 0) atomicAdd(dst + i27_1, Tmm[1]);
-        } else {
-            const int d0 = 6 * (p.nrc + mb);
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int j = 2 * q + e; const double v = e ? Tmm[1] : Tmm[0];
-                if (row_lt6 && j == 6) atomicAdd(gr + d0 + g, v * s1);
-                else if (row_lt6 && j < 6 && j >= g) { atomicAdd(Hrr + (size_t)(d0 + g) * n_r + d0 + j, v * s2); if (j != g) atomicAdd(Hrr + (size_t)(d0 + j) * n_r + d0 + g, v * s2); }
+        for (int k = 0; k < min(ASM_NST, nst); k++) issue(k);
+        int rbase = rA;
+        int4 mine = pl.mrun_info[min(rbase + lane, rB - 1)];
+        int jr = 0, left = __shfl_sync(0xffffffffu, mine.y, 0);
+        double Tmm[2] = {0, 0}, Tmf[2] = {0, 0};
+        for (int k = 0; k < nst; k++) {
+            const int slot = k % ASM_NST, nr = min(ASM_SROWS, E1 - E0 - k * ASM_SROWS);
+            mbar_wait(bar0 + 8 * slot, (k / ASM_NST) & 1);
+            const unsigned char *sb = ring + slot * STAGE;
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                const unsigned char *row = sb + r * ROWB;
+                const V2 xm = *reinterpret_cast<const V2 *>(row + off_m);
+                double m0 = (double)xm.x, m1 = (double)xm.y;                   // [Jm | r]
+                if (Hw && row_is6) { const double w = reinterpret_cast<const double *>(sb + ASM_SROWS * ROWB)[r * 4 + q]; m0 = w * m0; m1 = w * m1; }
+                dmma884(Tmm, m0, m0); dmma884(Tmm, m1, m1);                     // Hmm and, in column 6, gm
+                if (opt_f) { const V2 xf = *reinterpret_cast<const V2 *>(row + off_f); dmma884(Tmf, m0, (double)xf.x); dmma884(Tmf, m1, (double)xf.y); }      // W_m
+                if (--left == 0) {
+                    const int slot_m = __shfl_sync(0xffffffffu, mine.z, jr), mb = __shfl_sync(0xffffffffu, mine.w, jr);
+                    if (opt_f && slot_m >= 0 && in36)         // W_m: this run owns the slot
+                        *reinterpret_cast<double2 *>(W + (size_t)slot_m * 36 + g * 6 + j0) = make_double2(Tmf[0] * s2, Tmf[1] * s2);
+                    if (accM) {
+                        double *dst = accM + mb * ACC_LD;
+                        if (i27_0 >= 0) atomicAdd(dst + i27_0, Tmm[0]);
+                        if (i27_1 >= 0) atomicAdd(dst + i27_1, Tmm[1]);
+                    } else red_diag_block(Tmm, g, q, 6 * (p.nrc + mb), n_r, s1, s2, true, Hrr, gr);
+                    Tmm[0] = Tmm[1] = Tmf[0] = Tmf[1] = 0.0;
+                    if (++jr == 32 && rbase + 32 < rB) { rbase += 32; jr = 0; mine = pl.mrun_info[min(rbase + lane, rB - 1)]; }
+                    if (rbase + jr < rB) left = __shfl_sync(0xffffffffu, mine.y, jr);
+                }
             }
+            __syncwarp();
+            if (k + ASM_NST < nst) issue(k + ASM_NST);
         }
     }
     if (accM) { __syncthreads(); flush_diag_blocks(accM, p.nrm, p.nrc, n_r, s1, s2, Hrr, gr); }

@@ -94,7 +94,7 @@ struct aar_problem {
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
-    DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
+    DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm, d_pair_slot; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
     bool legacy_acc = false;                                                          // AAR_ASM=legacy: round-1 lane-per-observation kernel (A/B aid)
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
     DevBuf<double> d_fc, d_E, d_xinv;
@@ -193,23 +193,29 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
         return AAR_OK;
     }
     auto k1 = k_jac_project<JT, true>; auto k2 = k_asm_pairs<JT>; auto k3 = k_asm_mruns<JT>;
-    AsmPlan pl; pl.pair_info = p->d_pair_info.p; pl.mrun_info = p->d_mrun_info.p; pl.perm_fm = p->d_perm_fm.p; pl.npairs = p->npairs; pl.nmruns = p->nmruns;
+    AsmPlan pl; pl.pair_info = p->d_pair_info.p; pl.pair_slot = p->d_pair_slot.p; pl.mrun_info = p->d_mrun_info.p; pl.perm_fm = p->d_perm_fm.p;
+    pl.npairs = p->npairs; pl.nmruns = p->nmruns; pl.nperm = (int)p->d_perm_fm.n;
     pl.s1 = s1; pl.s2 = s2;
-    const size_t smem2 = (size_t)p->nrc * ACC_LD * sizeof(double), smem3 = (size_t)p->nrm * ACC_LD * sizeof(double);
-    pl.smem_acc = std::max(smem2, smem3) + 1024 <= p->smem_optin / AAR_ASM_MINBLOCKS;   // several CTAs per SM
+    // dynamic shared memory: [camera / marker accumulators] | mbarriers | per-warp rings of staged rows (aar_assemble.cuh)
+    const size_t ring2 = ASM_BAR_BYTES + asm_ring_bytes<JT>(JROW), ring3 = ASM_BAR_BYTES + asm_ring_bytes<JT>(ASM_MROW);
+    pl.smem_acc = std::max(asm_acc_bytes(p->nrc) + ring2, asm_acc_bytes(p->nrm) + ring3) <= p->smem_optin;
+    const size_t smem2 = ring2 + (pl.smem_acc ? asm_acc_bytes(p->nrc) : 0), smem3 = ring3 + (pl.smem_acc ? asm_acc_bytes(p->nrm) : 0);
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
-    if (pl.smem_acc && smem2 > 48 * 1024) CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    if (pl.smem_acc && smem3 > 48 * 1024) CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     LAUNCH(p, k1, grid1, PROJ_THREADS, smem1, p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, 0LL, N);
     prof_mark(p, 9);
-    const int per_sm = AAR_ASM_MINBLOCKS;
+    // every warp takes an equal share of the row stream: at least ~64 rows per warp, at most the resident CTAs of the device
+    const long long want = std::max<long long>(1, (N + 64LL * ASM_WARPS - 1) / (64LL * ASM_WARPS));
     if (p->npairs > 0) {
-        const int grid2 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * p->num_sms, ((long long)p->npairs + ASM_WARPS - 1) / ASM_WARPS));
-        LAUNCH(p, k2, grid2, ASM_THREADS, pl.smem_acc ? smem2 : 0, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+        int per_sm = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, ASM_THREADS, smem2));
+        const int grid2 = (int)std::min<long long>((long long)std::max(per_sm, 1) * p->num_sms, want);
+        LAUNCH(p, k2, grid2, ASM_THREADS, smem2, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
     }
     if (p->nmruns > 0) {
-        const int grid3 = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * p->num_sms, ((long long)p->nmruns + ASM_WARPS - 1) / ASM_WARPS));
-        LAUNCH(p, k3, grid3, ASM_THREADS, pl.smem_acc ? smem3 : 0, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+        int per_sm = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, ASM_THREADS, smem3));
+        const int grid3 = (int)std::min<long long>((long long)std::max(per_sm, 1) * p->num_sms, want);
+        LAUNCH(p, k3, grid3, ASM_THREADS, smem3, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
     }
     prof_mark(p, 8);
     return AAR_OK;
@@ -503,6 +509,9 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
             pair_info[(size_t)pr].y++;
         }
         UP(p->d_pair_info, pair_info);
+        std::vector<int> pair_slot((size_t)p->npairs);
+        for (int pr = 0; pr < p->npairs; pr++) pair_slot[(size_t)pr] = slot_c[(size_t)pair_info[(size_t)pr].x];
+        UP(p->d_pair_slot, pair_slot);
         std::vector<int> perm_fm; std::vector<int4> mrun_info;
         if (p->opt_m) {
             perm_fm.reserve((size_t)Nl); mrun_info.reserve((size_t)(ms_cum.empty() ? 0 : ms_cum.back()) + 16);

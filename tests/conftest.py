@@ -13,6 +13,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+PARITY_LOG = os.path.join(ROOT, "gpurun_out", "parity_achieved.jsonl")
+
+
+def parity_record(check, **values):
+    """Keeps the deviation a parity test ACHIEVED next to the bar it asserts: one JSON line per check
+    in gpurun_out/parity_achieved.jsonl (merged back from the GPU box; the round's copy lives in profiles/r2_parity.jsonl)."""
+    import json
+    import numpy as np
+    def plain(v):
+        if isinstance(v, (np.floating, np.integer)): return v.item()
+        if isinstance(v, np.ndarray): return v.tolist()
+        return v
+    rec = {"check": check}; rec.update({k: plain(v) for k, v in values.items()})
+    os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+    with open(PARITY_LOG, "a") as fh:
+        fh.write(json.dumps(rec) + "\n")
+    print("PARITY", json.dumps(rec))
+    return rec
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+K="bit_exact or config_flags or reduced_system or edge_cases or first_iterations or exact_staging or tensor_core or huber"
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$K" > gpurun_out/r2d_pytest_subset.txt 2>&1; tail -15 gpurun_out/r2d_pytest_subset.txt
+timeout 600 python tools/quick_time.py --workload cfg4 --frames 20000 --iters 6 --libs default > gpurun_out/r2d_variants.txt 2>&1
+grep "==\|ms/iter\|rror" gpurun_out/r2d_variants.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_asm" -c 2 -f -o gpurun_out/r2d_asm python tools/quick_time.py --workload cfg4 --frames 20000 --iters 1 > gpurun_out/r2d_ncu.log 2>&1
+tail -2 gpurun_out/r2d_ncu.log
