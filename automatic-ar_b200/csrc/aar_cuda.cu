@@ -13,7 +13,9 @@
 #include <memory>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sched.h>
 
 #include <cuda_runtime.h>
 #include <nccl.h> // types only; the library is dlopen'ed so single-GPU use needs no NCCL
@@ -88,15 +90,16 @@ struct aar_problem {
     int nrc = 0, nrm = 0, n_r = 0;
     long long n_vars = 0;
     long long nslots = 0; int max_slots = 0;
+    long long schur_fma = 0;                       // sum over local frames of 6 * n_f (n_f + 1) / 2, n_f = 6 * (blocks seen): the upper triangle of S -= E E^T
     // ---- device
     cudaStream_t stream = nullptr; bool own_stream = false;
     DevBuf<int> d_obs_f, d_obs_cm, d_slot_c, d_slot_m, d_frame_slot_ptr, d_slot_block;
     DevBuf<float4> d_und_a, d_und_b, d_raw_a, d_raw_b;
     DevBuf<int> d_frame_cs_cum, d_slot_frame, d_frame_block_slot, d_frame_obs_ptr, d_trk_iters, d_obs_pair;
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
-    DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm, d_pair_slot; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
+    DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm, d_pair_cam; DevBuf<double> d_cm_rep; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
     bool legacy_acc = false;                                                          // AAR_ASM=legacy: round-1 lane-per-observation kernel (A/B aid)
-    DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_cost;
+    DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_z0, d_trk_cost; bool trk_have_z0 = false; double track_ms = 0; long long track_runs = 0;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
@@ -119,7 +122,7 @@ struct aar_problem {
     ncclComm_t comm = nullptr;
     // ---- instrumentation
     long long launches = 0; bool profiling = false;
-    cudaEvent_t ev[12] = {}; double phase_ms[AAR_NUM_PHASES] = {};
+    cudaEvent_t ev[16] = {}; double phase_ms[AAR_NUM_PHASES] = {};
 };
 
 namespace {
@@ -140,6 +143,43 @@ int rank_of(const std::vector<int> &ids, int id) {
     if (it == ids.end() || *it != id) return -1;
     return (int)(it - ids.begin());
 }
+
+// ---- host-side parallel loops of aar_problem_create (plain std::thread: the library links nothing but the CUDA runtime)
+int host_threads(long long work) {
+    if (work < (1LL << 16)) return 1;
+    static int n = [] {
+        const char *e = getenv("AAR_HOST_THREADS");
+        if (e && atoi(e) > 0) return atoi(e);
+        cpu_set_t set; CPU_ZERO(&set);
+        int c = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(c, 64));
+    }();
+    return n;
+}
+template <class F> void parallel_for(long long n, int T, F fn) {      // fn(begin, end, thread index) over T contiguous chunks of [0, n)
+    if (T <= 1 || n <= 0) { fn(0, std::max<long long>(n, 0), 0); return; }
+    std::vector<std::thread> th; th.reserve((size_t)T - 1);
+    for (int t = 1; t < T; t++) th.emplace_back([&, t] { fn(n * t / T, n * (t + 1) / T, t); });
+    fn(0, n / T, 0);
+    for (auto &x : th) x.join();
+}
+// id -> index of a strictly ascending id list: arithmetic when the ids are consecutive, a dense table when their range is small
+struct IdMap {
+    const std::vector<int> &ids; int lo = 0; bool consecutive = true; std::vector<int> table;
+    explicit IdMap(const std::vector<int> &v) : ids(v) {
+        if (ids.empty()) return;
+        lo = ids.front();
+        for (size_t i = 0; i < ids.size(); i++) if (ids[i] != lo + (int)i) { consecutive = false; break; }
+        const long long range = (long long)ids.back() - lo + 1;
+        if (!consecutive && range <= (long long)(4 * ids.size() + (1 << 20))) { table.assign((size_t)range, -1); for (size_t i = 0; i < ids.size(); i++) table[(size_t)(ids[i] - lo)] = (int)i; }
+    }
+    int operator()(int id) const {
+        if (ids.empty()) return -1;
+        if (consecutive) { const long long k = (long long)id - lo; return k >= 0 && k < (long long)ids.size() ? (int)k : -1; }
+        if (!table.empty()) { const long long k = (long long)id - lo; return k >= 0 && k < (long long)table.size() ? table[(size_t)k] : -1; }
+        return rank_of(ids, id);
+    }
+};
 
 // column of a block in io_vec (multicam_mapper.cpp:815-817, 824-826, 833)
 long long col_cam(const aar_problem *p, int i) { if (!p->opt_c || i == p->root_cam) return -1; return 6LL * (i - (i > p->root_cam ? 1 : 0)); }
@@ -193,13 +233,21 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
         return AAR_OK;
     }
     auto k1 = k_jac_project<JT, true>; auto k2 = k_asm_pairs<JT>; auto k3 = k_asm_mruns<JT>;
-    AsmPlan pl; pl.pair_info = p->d_pair_info.p; pl.pair_slot = p->d_pair_slot.p; pl.mrun_info = p->d_mrun_info.p; pl.perm_fm = p->d_perm_fm.p;
-    pl.npairs = p->npairs; pl.nmruns = p->nmruns; pl.nperm = (int)p->d_perm_fm.n;
+    AsmPlan pl; pl.pair_info = p->d_pair_info.p; pl.pair_cam = p->d_pair_cam.p; pl.npairs = p->npairs; pl.mrun_info = p->d_mrun_info.p; pl.perm_fm = p->d_perm_fm.p;
+    pl.nmruns = p->nmruns; pl.nperm = (int)p->d_perm_fm.n;
     pl.s1 = s1; pl.s2 = s2;
-    // dynamic shared memory: [camera / marker accumulators] | mbarriers | per-warp rings of staged rows (aar_assemble.cuh)
-    const size_t ring2 = ASM_BAR_BYTES + asm_ring_bytes<JT>(JROW), ring3 = ASM_BAR_BYTES + asm_ring_bytes<JT>(ASM_MROW);
+    // dynamic shared memory (aar_assemble.cuh): [camera / marker accumulators] | mbarriers | per-warp rings
+    pl.ring_pairs = sizeof(JT) == 4 ? 3 : 2;      // 3 CTAs of 8 warps per SM with float staging
+    const size_t ring2 = ASM_BAR_BYTES + (size_t)ASM_WARPS * pl.ring_pairs * asm_stage_bytes<JT>(JROW), ring3 = ASM_BAR_BYTES + asm_ring_bytes<JT>(ASM_MROW);
     pl.smem_acc = std::max(asm_acc_bytes(p->nrc) + ring2, asm_acc_bytes(p->nrm) + ring3) <= p->smem_optin;
     const size_t smem2 = ring2 + (pl.smem_acc ? asm_acc_bytes(p->nrc) : 0), smem3 = ring3 + (pl.smem_acc ? asm_acc_bytes(p->nrm) : 0);
+    // camera x marker blocks: ASM_CM_REPLICAS copies of a [nrc][nrm][36] table (up to 256 MB; larger rigs add straight into the reduced matrix)
+    const size_t cm_n = (size_t)p->nrc * p->nrm * 36;
+    const bool use_rep = p->opt_c && p->opt_m && cm_n > 0 && cm_n * ASM_CM_REPLICAS * sizeof(double) <= (256u << 20);
+    if (use_rep) {
+        if (p->d_cm_rep.n < cm_n * ASM_CM_REPLICAS) CU(p->d_cm_rep.alloc(cm_n * ASM_CM_REPLICAS));
+        CU(cudaMemsetAsync(p->d_cm_rep.p, 0, cm_n * ASM_CM_REPLICAS * sizeof(double), p->stream));
+    }
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
@@ -210,8 +258,10 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     if (p->npairs > 0) {
         int per_sm = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, ASM_THREADS, smem2));
         const int grid2 = (int)std::min<long long>((long long)std::max(per_sm, 1) * p->num_sms, want);
-        LAUNCH(p, k2, grid2, ASM_THREADS, smem2, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+        LAUNCH(p, k2, grid2, ASM_THREADS, smem2, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_Hf.p, p->d_W.p, p->d_Hrr.p, p->d_gr.p, use_rep ? p->d_cm_rep.p : nullptr);
+        if (use_rep) LAUNCH(p, k_cm_reduce, cdiv((long long)cm_n, 256), 256, 0, p->nrc, p->nrm, p->n_r, s2, p->d_cm_rep.p, p->d_Hrr.p);
     }
+    prof_mark(p, 12);
     if (p->nmruns > 0) {
         int per_sm = 1; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, ASM_THREADS, smem3));
         const int grid3 = (int)std::min<long long>((long long)std::max(per_sm, 1) * p->num_sms, want);
@@ -275,7 +325,9 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
         // two CTAs per SM, at most two full waves (no tail wave), at least a few pipeline stages per CTA
         const int nchunks = std::max(1, std::min((2 * AAR_SY_MINBLOCKS * p->num_sms) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
+        prof_mark(p, 10);
         LAUNCH(p, k_schur_syrk, ntiles * nchunks, SY_THREADS, SY_SMEM, p->dp, nb, tiles_side, nchunks, p->d_frame_block_slot.p, p->d_E.p, S);
+        prof_mark(p, 11);
     }
     return AAR_OK;
 }
@@ -374,36 +426,58 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     // ---- fill_iteration_arrays (multicam_mapper.cpp:345-377): frame id ^, cam id ^, detection order;
     // detections of unknown cameras / markers are erased.  (Detections of a frame without an object pose make
     // the reference throw std::out_of_range in project_marker; they are dropped here.)
+    // The host passes below run on all the cores the process may use (25.6 M detections at BASELINE cfg 4).
     const long long nd = d->num_detections;
-    std::vector<long long> keep; keep.reserve((size_t)nd);
+    const IdMap fmap(p->frame_ids), cmap(p->cam_ids), mmap(p->marker_ids);
     std::vector<int> kf((size_t)nd), kc((size_t)nd), km((size_t)nd);
-    for (long long i = 0; i < nd; i++) {
-        int fi = rank_of(p->frame_ids, d->det_frame[i]), ci = rank_of(p->cam_ids, d->det_cam[i]), mi = rank_of(p->marker_ids, d->det_marker[i]);
-        if (fi < 0 || ci < 0 || mi < 0) continue;
-        kf[(size_t)i] = fi; kc[(size_t)i] = ci; km[(size_t)i] = mi; keep.push_back(i);
+    std::vector<long long> keep;
+    {
+        const int T = host_threads(nd);
+        std::vector<long long> cnt((size_t)T + 1, 0);
+        parallel_for(nd, T, [&](long long b0, long long b1, int t) {
+            long long n = 0;
+            for (long long i = b0; i < b1; i++) {
+                const int fi = fmap(d->det_frame[i]), ci = cmap(d->det_cam[i]), mi = mmap(d->det_marker[i]);
+                const bool ok = fi >= 0 && ci >= 0 && mi >= 0;
+                kf[(size_t)i] = ok ? fi : -1; kc[(size_t)i] = ci; km[(size_t)i] = mi; n += ok;
+            }
+            cnt[(size_t)t + 1] = n;
+        });
+        for (int t = 0; t < T; t++) cnt[(size_t)t + 1] += cnt[(size_t)t];
+        keep.resize((size_t)cnt[(size_t)T]);
+        parallel_for(nd, T, [&](long long b0, long long b1, int t) {
+            long long w = cnt[(size_t)t];
+            for (long long i = b0; i < b1; i++) if (kf[(size_t)i] >= 0) keep[(size_t)w++] = i;
+        });
     }
     auto before = [&](long long a, long long b) { return kf[(size_t)a] != kf[(size_t)b] ? kf[(size_t)a] < kf[(size_t)b] : kc[(size_t)a] < kc[(size_t)b]; };
     if (!std::is_sorted(keep.begin(), keep.end(), before)) // aruco.detections order is already (frame, cam)
-    std::stable_sort(keep.begin(), keep.end(), [&](long long a, long long b) { return kf[(size_t)a] != kf[(size_t)b] ? kf[(size_t)a] < kf[(size_t)b] : kc[(size_t)a] < kc[(size_t)b]; });
+        std::stable_sort(keep.begin(), keep.end(), before);
     p->N = (long long)keep.size();
     p->g_frame.resize((size_t)p->N); p->g_cam.resize((size_t)p->N); p->g_marker.resize((size_t)p->N); p->g_hasjac.assign((size_t)p->N, 1);
-    for (long long o = 0; o < p->N; o++) { long long i = keep[(size_t)o]; p->g_frame[(size_t)o] = kf[(size_t)i]; p->g_cam[(size_t)o] = kc[(size_t)i]; p->g_marker[(size_t)o] = km[(size_t)i]; }
-    // a repeated (frame, cam, marker) overwrites the earlier entry of the inverted indices (:368-370):
-    // only the LAST occurrence contributes Jacobian rows
-    for (long long o = 0; o < p->N;) {
-        long long e = o;
-        while (e < p->N && p->g_frame[(size_t)e] == p->g_frame[(size_t)o] && p->g_cam[(size_t)e] == p->g_cam[(size_t)o]) e++;
-        if (e - o > 1) {
-            std::map<int, long long> last;
-            for (long long q = o; q < e; q++) last[p->g_marker[(size_t)q]] = q;
-            for (long long q = o; q < e; q++) if (last[p->g_marker[(size_t)q]] != q) p->g_hasjac[(size_t)q] = 0;
-        }
-        o = e;
-    }
-    // ---- frame shard: contiguous frame ranges balanced by observation count (SURVEY 8e)
+    parallel_for(p->N, host_threads(p->N), [&](long long b0, long long b1, int) {
+        for (long long o = b0; o < b1; o++) { const long long i = keep[(size_t)o]; p->g_frame[(size_t)o] = kf[(size_t)i]; p->g_cam[(size_t)o] = kc[(size_t)i]; p->g_marker[(size_t)o] = km[(size_t)i]; }
+    });
+    { std::vector<int>().swap(kf); std::vector<int>().swap(kc); std::vector<int>().swap(km); }
     std::vector<long long> frame_ptr((size_t)p->F + 1, 0);
     for (long long o = 0; o < p->N; o++) frame_ptr[(size_t)p->g_frame[(size_t)o] + 1]++;
     for (int f = 0; f < p->F; f++) frame_ptr[(size_t)f + 1] += frame_ptr[(size_t)f];
+    // a repeated (frame, cam, marker) overwrites the earlier entry of the inverted indices (:368-370):
+    // only the LAST occurrence contributes Jacobian rows
+    parallel_for(p->F, host_threads(p->N), [&](long long f0, long long f1, int) {
+        std::vector<long long> stamp((size_t)p->M, -1), lastidx((size_t)p->M, 0);
+        for (long long o = frame_ptr[(size_t)f0]; o < frame_ptr[(size_t)f1];) {
+            long long e = o;
+            while (e < frame_ptr[(size_t)f1] && p->g_frame[(size_t)e] == p->g_frame[(size_t)o] && p->g_cam[(size_t)e] == p->g_cam[(size_t)o]) e++;
+            for (long long q = o; q < e; q++) {
+                const size_t m = (size_t)p->g_marker[(size_t)q];
+                if (stamp[m] == o) p->g_hasjac[(size_t)lastidx[m]] = 0;
+                stamp[m] = o; lastidx[m] = q;
+            }
+            o = e;
+        }
+    });
+    // ---- frame shard: contiguous frame ranges balanced by observation count (SURVEY 8e)
     auto boundary = [&](int r) -> int {
         if (r <= 0) return 0; if (r >= p->world) return p->F;
         long long target = p->N * r / p->world;
@@ -415,44 +489,62 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     const int Fl = p->f_end - p->f_begin; const long long Nl = p->o_end - p->o_begin;
 
     // ---- W slots: per local frame, the distinct active camera blocks seen (order of first appearance), then the
-    // distinct active marker blocks; cs_cum / ms_cum are the running numbers of camera / marker slots
-    std::vector<int> slot_ptr((size_t)Fl + 1, 0), cs_cum((size_t)Fl + 1, 0), ms_cum((size_t)Fl + 1, 0), slot_block, slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
-    p->max_slots = 0; p->max_ms = 0;
+    // distinct active marker blocks; cs_cum / ms_cum are the running numbers of camera / marker slots.
+    // Two passes over the local frames (count, prefix sum, fill), both parallel.
     if (Nl >= (1LL << 31) - 1) { set_err("more than 2^31 observations on one rank"); return AAR_ERR_UNSUPPORTED; }
-    {
-        std::vector<int> seen((size_t)(p->nrc + p->nrm), -1);
-        for (int f = 0; f < Fl; f++) {
-            const int base = (int)slot_block.size();
+    const int nblk_r = p->nrc + p->nrm;
+    std::vector<int> slot_ptr((size_t)Fl + 1, 0), cs_cum((size_t)Fl + 1, 0), ms_cum((size_t)Fl + 1, 0), slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
+    const bool slots_c = p->opt_f && p->opt_c, slots_m = p->opt_f && p->opt_m;
+    const int Tf = host_threads(Nl);
+    parallel_for(Fl, Tf, [&](long long f0, long long f1, int) {
+        std::vector<long long> stamp((size_t)std::max(nblk_r, 1), -1);
+        for (long long f = f0; f < f1; f++) {
             const long long o0 = frame_ptr[(size_t)(p->f_begin + f)], o1 = frame_ptr[(size_t)(p->f_begin + f) + 1];
-            std::vector<int> touched;
-            if (p->opt_f && p->opt_c)
+            int ncs = 0, nms = 0;
+            for (long long o = o0; o < o1; o++) {
+                const int c = p->g_cam[(size_t)o], m = p->g_marker[(size_t)o];
+                if (slots_c && c != p->root_cam) { const size_t bk = (size_t)(c - (c > p->root_cam ? 1 : 0)); if (stamp[bk] != f) { stamp[bk] = f; ncs++; } }
+                if (slots_m && m != p->root_marker) { const size_t bk = (size_t)(p->nrc + m - (m > p->root_marker ? 1 : 0)); if (stamp[bk] != f) { stamp[bk] = f; nms++; } }
+            }
+            cs_cum[(size_t)f + 1] = ncs; ms_cum[(size_t)f + 1] = nms;
+        }
+    });
+    p->max_slots = 0; p->max_ms = 0; p->schur_fma = 0;
+    for (int f = 0; f < Fl; f++) {
+        const int ncs = cs_cum[(size_t)f + 1], nms = ms_cum[(size_t)f + 1];
+        slot_ptr[(size_t)f + 1] = slot_ptr[(size_t)f] + ncs + nms;
+        cs_cum[(size_t)f + 1] += cs_cum[(size_t)f]; ms_cum[(size_t)f + 1] += ms_cum[(size_t)f];
+        p->max_slots = std::max(p->max_slots, ncs + nms); p->max_ms = std::max(p->max_ms, nms);
+        const long long nf = 6LL * (ncs + nms); p->schur_fma += 6 * nf * (nf + 1) / 2;
+    }
+    p->nslots = (long long)slot_ptr[(size_t)Fl];
+    std::vector<int> slot_block((size_t)p->nslots), slot_frame((size_t)p->nslots), frame_block_slot((size_t)std::max(Fl, 1) * std::max(nblk_r, 1));
+    parallel_for(Fl, Tf, [&](long long f0, long long f1, int) {
+        std::vector<int> seen((size_t)std::max(nblk_r, 1), -1);
+        std::fill(frame_block_slot.begin() + (size_t)f0 * std::max(nblk_r, 1), frame_block_slot.begin() + (size_t)f1 * std::max(nblk_r, 1), -1);
+        for (long long f = f0; f < f1; f++) {
+            const long long o0 = frame_ptr[(size_t)(p->f_begin + f)], o1 = frame_ptr[(size_t)(p->f_begin + f) + 1];
+            int next = slot_ptr[(size_t)f];
+            const int first = next;
+            if (slots_c)
                 for (long long o = o0; o < o1; o++) {
                     const int c = p->g_cam[(size_t)o];
                     if (c == p->root_cam) continue;
                     const int bk = c - (c > p->root_cam ? 1 : 0);
-                    if (seen[(size_t)bk] < 0) { seen[(size_t)bk] = (int)slot_block.size(); slot_block.push_back(bk); touched.push_back(bk); }
+                    if (seen[(size_t)bk] < first) { seen[(size_t)bk] = next; slot_block[(size_t)next++] = bk; }
                     slot_c[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
                 }
-            const int ncs = (int)slot_block.size() - base;
-            if (p->opt_f && p->opt_m)
+            if (slots_m)
                 for (long long o = o0; o < o1; o++) {
                     const int m = p->g_marker[(size_t)o];
                     if (m == p->root_marker) continue;
                     const int bk = p->nrc + m - (m > p->root_marker ? 1 : 0);
-                    if (seen[(size_t)bk] < 0) { seen[(size_t)bk] = (int)slot_block.size(); slot_block.push_back(bk); touched.push_back(bk); }
+                    if (seen[(size_t)bk] < first) { seen[(size_t)bk] = next; slot_block[(size_t)next++] = bk; }
                     slot_m[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
                 }
-            for (int bk : touched) seen[(size_t)bk] = -1;
-            const int nms = (int)slot_block.size() - base - ncs;
-            slot_ptr[(size_t)f + 1] = (int)slot_block.size();
-            cs_cum[(size_t)f + 1] = cs_cum[(size_t)f] + ncs; ms_cum[(size_t)f + 1] = ms_cum[(size_t)f] + nms;
-            p->max_slots = std::max(p->max_slots, ncs + nms); p->max_ms = std::max(p->max_ms, nms);
+            for (int sl = first; sl < next; sl++) { slot_frame[(size_t)sl] = (int)f; frame_block_slot[(size_t)f * nblk_r + slot_block[(size_t)sl]] = sl; }
         }
-    }
-    p->nslots = (long long)slot_block.size();
-    std::vector<int> slot_frame((size_t)p->nslots), frame_block_slot((size_t)std::max(Fl, 1) * std::max(p->nrc + p->nrm, 1), -1);
-    for (int f = 0; f < Fl; f++)
-        for (int sl = slot_ptr[(size_t)f]; sl < slot_ptr[(size_t)f + 1]; sl++) { slot_frame[(size_t)sl] = f; frame_block_slot[(size_t)f * (p->nrc + p->nrm) + slot_block[(size_t)sl]] = sl; }
+    });
 
     if (host_only) { guard.release(); *out = p; return AAR_OK; }   // aar_shard_plan: row map and shard only
     // ---- device
@@ -472,13 +564,15 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
 
     std::vector<int> obs_f((size_t)Nl), obs_cm((size_t)Nl);
     std::vector<float4> raw_a((size_t)Nl), raw_b((size_t)Nl);
-    for (long long o = 0; o < Nl; o++) {
-        const long long g = p->o_begin + o, i = keep[(size_t)g];
-        obs_f[(size_t)o] = p->g_frame[(size_t)g] - p->f_begin;
-        obs_cm[(size_t)o] = p->g_cam[(size_t)g] | (p->g_marker[(size_t)g] << 12) | (p->g_hasjac[(size_t)g] ? 0 : (int)0x80000000u);
-        const float *xy = d->det_xy + 8 * i;
-        raw_a[(size_t)o] = make_float4(xy[0], xy[1], xy[2], xy[3]); raw_b[(size_t)o] = make_float4(xy[4], xy[5], xy[6], xy[7]);
-    }
+    parallel_for(Nl, host_threads(Nl), [&](long long b0, long long b1, int) {
+        for (long long o = b0; o < b1; o++) {
+            const long long g = p->o_begin + o, i = keep[(size_t)g];
+            obs_f[(size_t)o] = p->g_frame[(size_t)g] - p->f_begin;
+            obs_cm[(size_t)o] = p->g_cam[(size_t)g] | (p->g_marker[(size_t)g] << 12) | (p->g_hasjac[(size_t)g] ? 0 : (int)0x80000000u);
+            const float *xy = d->det_xy + 8 * i;
+            raw_a[(size_t)o] = make_float4(xy[0], xy[1], xy[2], xy[3]); raw_b[(size_t)o] = make_float4(xy[4], xy[5], xy[6], xy[7]);
+        }
+    });
     // (frame, camera) pairs: runs of consecutive observations in row order; every perturbation of inv(Tc) * To is
     // evaluated once per pair (k_pair_tab) instead of once per observation
     std::vector<int> obs_pair((size_t)Nl); std::vector<int2> pair_fc;
@@ -508,10 +602,11 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
             if (o == 0 || obs_pair[(size_t)o - 1] != pr) pair_info[(size_t)pr] = make_int4((int)o, 0, pair_fc[(size_t)pr].x, pair_fc[(size_t)pr].y);
             pair_info[(size_t)pr].y++;
         }
-        UP(p->d_pair_info, pair_info);
-        std::vector<int> pair_slot((size_t)p->npairs);
-        for (int pr = 0; pr < p->npairs; pr++) pair_slot[(size_t)pr] = slot_c[(size_t)pair_info[(size_t)pr].x];
-        UP(p->d_pair_slot, pair_slot);
+        {   // descriptors of k_asm_pairs: (first row, rows, frame, W slot) and the camera of every pair
+            std::vector<int> pair_cam((size_t)p->npairs);
+            for (int pr = 0; pr < p->npairs; pr++) { int4 &pi = pair_info[(size_t)pr]; pair_cam[(size_t)pr] = pi.w; pi.w = slot_c[(size_t)pi.x]; }
+            UP(p->d_pair_info, pair_info); UP(p->d_pair_cam, pair_cam);
+        }
         std::vector<int> perm_fm; std::vector<int4> mrun_info;
         if (p->opt_m) {
             perm_fm.reserve((size_t)Nl); mrun_info.reserve((size_t)(ms_cum.empty() ? 0 : ms_cum.back()) + 16);
@@ -581,21 +676,9 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         CU(cudaMemcpyAsync(p->d_und_a.p, p->d_raw_a.p, (size_t)Nl * sizeof(float4), cudaMemcpyDeviceToDevice, p->stream));
         CU(cudaMemcpyAsync(p->d_und_b.p, p->d_raw_b.p, (size_t)Nl * sizeof(float4), cudaMemcpyDeviceToDevice, p->stream));
     } else if (Nl > 0) {
-        // view raw_a as 2*Nl float2 points whose observation is i>>1; reuse k_undistort with a shifted index map:
-        // simplest is a temporary interleaved buffer of 4*Nl points in observation order.
-        DevBuf<float2> tin, tout;
-        CU(tin.alloc(4 * (size_t)Nl)); CU(tout.alloc(4 * (size_t)Nl));
-        std::vector<float2> pts(4 * (size_t)Nl);
-        for (long long o = 0; o < Nl; o++) { const float *xy = d->det_xy + 8 * keep[(size_t)(p->o_begin + o)]; for (int k = 0; k < 4; k++) pts[4 * (size_t)o + k] = make_float2(xy[2 * k], xy[2 * k + 1]); }
-        CU(cudaMemcpyAsync(tin.p, pts.data(), pts.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
-        LAUNCH(p, k_undistort, cdiv(4 * Nl, 256), 256, 0, 4 * Nl, tin.p, p->d_obs_cm.p, p->d_K9.p, p->d_dist5.p, tout.p);
-        CU(cudaMemcpyAsync(pts.data(), tout.p, pts.size() * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
-        CU(cudaStreamSynchronize(p->stream));
-        std::vector<float4> ua((size_t)Nl), ub((size_t)Nl);
-        for (long long o = 0; o < Nl; o++) { const float2 *q = &pts[4 * (size_t)o]; ua[(size_t)o] = make_float4(q[0].x, q[0].y, q[1].x, q[1].y); ub[(size_t)o] = make_float4(q[2].x, q[2].y, q[3].x, q[3].y); }
-        CU(cudaMemcpyAsync(p->d_und_a.p, ua.data(), ua.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
-        CU(cudaMemcpyAsync(p->d_und_b.p, ub.data(), ub.size() * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
-        CU(cudaStreamSynchronize(p->stream));
+        // raw_a / raw_b viewed as 2 Nl float2 points each: point i belongs to observation i >> 1
+        LAUNCH(p, k_undistort, cdiv(2 * Nl, 256), 256, 0, 2 * Nl, 1, reinterpret_cast<const float2 *>(p->d_raw_a.p), p->d_obs_cm.p, p->d_K9.p, p->d_dist5.p, reinterpret_cast<float2 *>(p->d_und_a.p));
+        LAUNCH(p, k_undistort, cdiv(2 * Nl, 256), 256, 0, 2 * Nl, 1, reinterpret_cast<const float2 *>(p->d_raw_b.p), p->d_obs_cm.p, p->d_K9.p, p->d_dist5.p, reinterpret_cast<float2 *>(p->d_und_b.p));
     }
     { const char *e = getenv("AAR_FORCE_EXACT_STAGING"); p->force_exact_staging = e && *e == '1'; }   // test hook: FP64 staging of the Jacobian block
     CU(cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
@@ -909,7 +992,9 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
                     cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms;
                     cudaEventElapsedTime(&ms, p->ev[7], p->ev[9]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
                     cudaEventElapsedTime(&ms, p->ev[9], p->ev[8]); p->phase_ms[7] += ms;
+                    if (!p->legacy_acc && p->npairs > 0) { cudaEventElapsedTime(&ms, p->ev[9], p->ev[12]); p->phase_ms[10] += ms; cudaEventElapsedTime(&ms, p->ev[12], p->ev[8]); p->phase_ms[11] += ms; }
                 }
+                if (p->opt_f && p->dp.F > 0 && p->n_r > 0 && p->nslots > 0) { cudaEventElapsedTime(&ms, p->ev[10], p->ev[11]); p->phase_ms[8] += ms; p->phase_ms[9] += 1; }
                 cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
                 cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
                 cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->phase_ms[3] += ms;
@@ -983,27 +1068,74 @@ int aar_lm_solve(aar_problem *p, double *z, const aar_lm_params *params, aar_lm_
     return aar_lm_end(p, z);
 }
 
-int aar_track_batch(aar_problem *p, double *z6, const aar_lm_params *params, double *final_cost, int32_t *iterations) {
-    if (!p || !z6) return AAR_ERR_INVALID;
-    CU(cudaSetDevice(p->device));
-    aar_lm_params P; if (params) P = *params; else aar_lm_default_params(&P);
+// MultiCamMapper::track() for all local frames: upload the start poses / run the per-frame solves / read the results back.
+// The three steps are separate entry points so that a caller whose poses already live on the device (bench.py: `value`) can
+// time the solves alone; aar_track_batch is the host-buffer call of the reference boundary (mcm.cpp:430-443).
+static int track_alloc(aar_problem *p) {
     const int F = p->dp.F;
-    if (F == 0) return AAR_OK;
     if (!p->d_trk_z.n) {
         CU(p->d_trk_cam_inv.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_trk_Y.alloc((size_t)p->M * 12));
-        CU(p->d_trk_z.alloc((size_t)F * 6)); CU(p->d_trk_cost.alloc((size_t)F)); CU(p->d_trk_iters.alloc((size_t)F));
+        CU(p->d_trk_z.alloc((size_t)F * 6)); CU(p->d_trk_z0.alloc((size_t)F * 6)); CU(p->d_trk_cost.alloc((size_t)F)); CU(p->d_trk_iters.alloc((size_t)F));
     }
+    return AAR_OK;
+}
+int aar_track_upload(aar_problem *p, const double *z6) {
+    if (!p || !z6) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    if (p->dp.F == 0) return AAR_OK;
+    int rc = track_alloc(p); if (rc) return rc;
+    CU(cudaMemcpyAsync(p->d_trk_z0.p, z6, (size_t)p->dp.F * 6 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    p->trk_have_z0 = true;
+    return AAR_OK;
+}
+int aar_track_run(aar_problem *p, const aar_lm_params *params) {
+    if (!p) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    const int F = p->dp.F;
+    if (F == 0) return AAR_OK;
+    if (!p->trk_have_z0) { set_err("aar_track_run without aar_track_upload"); return AAR_ERR_INVALID; }
+    aar_lm_params P; if (params) P = *params; else aar_lm_default_params(&P);
     // the rig is the one the handle was created with (camera / marker transforms are not optimised by track())
     LAUNCH(p, k_track_prepare, cdiv((long long)p->C + p->M, 128), 128, 0, p->dp, p->d_trk_cam_inv.p, p->d_trk_Y.p);
-    CU(cudaMemcpyAsync(p->d_trk_z.p, z6, (size_t)F * 6 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_trk_z.p, p->d_trk_z0.p, (size_t)F * 6 * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     TrackParams tp; tp.max_iters = P.max_iters; tp.min_error = P.min_error; tp.min_step_error_diff = P.min_step_error_diff;
     tp.min_average_step_error_diff = P.min_average_step_error_diff; tp.tau = P.tau; tp.der_epsilon = P.der_epsilon; tp.huber = p->huber;
-    LAUNCH(p, k_track, cdiv(F, TRK_WARPS), TRK_WARPS * 32, 0, p->dp, tp, p->d_frame_obs_ptr.p, p->d_trk_cam_inv.p, p->d_trk_Y.p, p->d_trk_z.p, p->d_trk_cost.p, p->d_trk_iters.p);
-    CU(cudaMemcpyAsync(z6, p->d_trk_z.p, (size_t)F * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    if (final_cost) CU(cudaMemcpyAsync(final_cost, p->d_trk_cost.p, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    if (iterations) CU(cudaMemcpyAsync(iterations, p->d_trk_iters.p, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    const size_t smem = track_cta_smem(p->C);
+    const char *e = getenv("AAR_TRACK");
+    prof_mark(p, 13);
+    if (smem <= p->smem_optin && !(e && !strcmp(e, "warp"))) {      // one CTA per frame, T1 = inv(Tc) * To once per camera and pose variant
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_track_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(p, k_track_cta, F, TRKB_THREADS, smem, p->dp, tp, p->d_frame_obs_ptr.p, p->d_trk_cam_inv.p, p->d_trk_Y.p, p->d_trk_z.p, p->d_trk_cost.p, p->d_trk_iters.p);
+    } else
+        LAUNCH(p, k_track, cdiv(F, TRK_WARPS), TRK_WARPS * 32, 0, p->dp, tp, p->d_frame_obs_ptr.p, p->d_trk_cam_inv.p, p->d_trk_Y.p, p->d_trk_z.p, p->d_trk_cost.p, p->d_trk_iters.p);
+    prof_mark(p, 14);
+    CU(cudaGetLastError());
+    if (p->profiling) { CU(cudaEventSynchronize(p->ev[14])); float ms; cudaEventElapsedTime(&ms, p->ev[13], p->ev[14]); p->track_ms += ms; p->track_runs++; }
+    return AAR_OK;
+}
+int aar_track_download(aar_problem *p, double *z6, double *final_cost, int32_t *iterations) {
+    if (!p) return AAR_ERR_INVALID;
+    CU(cudaSetDevice(p->device));
+    const int F = p->dp.F;
+    if (F > 0) {
+        if (z6) CU(cudaMemcpyAsync(z6, p->d_trk_z.p, (size_t)F * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (final_cost) CU(cudaMemcpyAsync(final_cost, p->d_trk_cost.p, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (iterations) CU(cudaMemcpyAsync(iterations, p->d_trk_iters.p, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    }
     CU(cudaStreamSynchronize(p->stream));
     CU(cudaGetLastError());
+    return AAR_OK;
+}
+int aar_track_batch(aar_problem *p, double *z6, const aar_lm_params *params, double *final_cost, int32_t *iterations) {
+    if (!p || !z6) return AAR_ERR_INVALID;
+    int rc;
+    if ((rc = aar_track_upload(p, z6))) return rc;
+    if ((rc = aar_track_run(p, params))) return rc;
+    return aar_track_download(p, z6, final_cost, iterations);
+}
+int aar_track_ms(const aar_problem *p, double *ms, int64_t *runs) {
+    if (!p) return AAR_ERR_INVALID;
+    if (ms) *ms = p->track_ms; if (runs) *runs = p->track_runs;
     return AAR_OK;
 }
 
@@ -1027,7 +1159,12 @@ int aar_comm_init(aar_problem *p, const void *id128) {
 }
 
 int64_t aar_kernel_launches(const aar_problem *p) { return p ? p->launches : 0; }
-int aar_set_profiling(aar_problem *p, int32_t on) { if (!p) return AAR_ERR_INVALID; p->profiling = on != 0; for (double &m : p->phase_ms) m = 0; return AAR_OK; }
+int aar_problem_stats(const aar_problem *p, int64_t *out) {
+    if (!p || !out) return AAR_ERR_INVALID;
+    out[0] = p->nslots; out[1] = p->npairs; out[2] = p->nmruns; out[3] = p->schur_fma; out[4] = 0; out[5] = p->max_slots; out[6] = p->f_begin; out[7] = p->f_end;
+    return AAR_OK;
+}
+int aar_set_profiling(aar_problem *p, int32_t on) { if (!p) return AAR_ERR_INVALID; p->profiling = on != 0; for (double &m : p->phase_ms) m = 0; p->track_ms = 0; p->track_runs = 0; return AAR_OK; }
 int aar_get_phase_ms(const aar_problem *p, double *ms) {
     if (!p || !ms) return AAR_ERR_INVALID;
     for (int i = 0; i < AAR_NUM_PHASES; i++) ms[i] = p->phase_ms[i];

@@ -362,10 +362,10 @@ __global__ void k_lm_decide(LmState *st, const double *__restrict__ red, int n_r
 
 // one-off device undistortion pass — cv::undistortPoints(..., K, dist, noArray, K) as called by
 // remove_distortions (mcm.cpp:554-578): 5 fixed-point iterations in double, float32 in/out.
-__global__ void k_undistort(long long n4, const float2 *__restrict__ in, const int *__restrict__ obs_cm, const double *__restrict__ K9, const double *__restrict__ dist5, float2 *__restrict__ out) {
+__global__ void k_undistort(long long n4, int obs_shift /* point i belongs to observation i >> obs_shift */, const float2 *__restrict__ in, const int *__restrict__ obs_cm, const double *__restrict__ K9, const double *__restrict__ dist5, float2 *__restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const int c = obs_cam(obs_cm[i >> 2]);
+    const int c = obs_cam(obs_cm[i >> obs_shift]);
     const double *K = K9 + 9 * (size_t)c, *k = dist5 + 5 * (size_t)c;
     const double fx = K[0], fy = K[4], ifx = 1. / fx, ify = 1. / fy, cx = K[2], cy = K[5];
     float2 uv = in[i];

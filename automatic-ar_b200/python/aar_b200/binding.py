@@ -25,8 +25,8 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 EXPORTS = ["aar_lm_default_params", "aar_problem_create", "aar_problem_destroy", "aar_last_error", "aar_num_vars",
            "aar_num_observations", "aar_num_local_observations", "aar_jacobian_nnz", "aar_index_maps", "aar_get_observations",
            "aar_mats2evec", "aar_evec2mats", "aar_eval_residual", "aar_eval_jacobian", "aar_reduced_system", "aar_lm_solve",
-           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_shard_plan", "aar_row_map", "aar_comm_unique_id", "aar_comm_init",
-           "aar_kernel_launches", "aar_set_profiling", "aar_get_phase_ms"]
+           "aar_lm_begin", "aar_lm_iterate", "aar_lm_end", "aar_track_batch", "aar_track_upload", "aar_track_run", "aar_track_download", "aar_track_ms", "aar_shard_plan", "aar_row_map", "aar_comm_unique_id", "aar_comm_init",
+           "aar_kernel_launches", "aar_set_profiling", "aar_get_phase_ms", "aar_problem_stats"]
 
 
 class AarError(RuntimeError):
@@ -255,6 +255,24 @@ class Problem:
         _chk(lib().aar_track_batch(self.h, _vp(z), C.byref(p), _vp(cost), _vp(iters)), "aar_track_batch")
         return z, cost, iters
 
+    def track_upload(self, z6):
+        z = np.ascontiguousarray(z6, np.float64).reshape(-1, 6)
+        _chk(lib().aar_track_upload(self.h, _vp(z)), "aar_track_upload")
+
+    def track_run(self, params=None):
+        p = params if params is not None else self.default_params()
+        _chk(lib().aar_track_run(self.h, C.byref(p)), "aar_track_run")
+
+    def track_download(self, n_frames):
+        z = np.zeros((n_frames, 6)); cost = np.zeros(n_frames); iters = np.zeros(n_frames, np.int32)
+        _chk(lib().aar_track_download(self.h, _vp(z), _vp(cost), _vp(iters)), "aar_track_download")
+        return z, cost, iters
+
+    def track_ms(self):
+        ms = C.c_double(0); runs = C.c_int64(0)
+        _chk(lib().aar_track_ms(self.h, C.byref(ms), C.byref(runs)), "aar_track_ms")
+        return ms.value, runs.value
+
     def lm_begin(self, z0=None, params=None):
         """z0 = None restarts from the z0 of the previous lm_begin (device resident, no copy)."""
         z = None if z0 is None else np.ascontiguousarray(z0, np.float64)
@@ -273,13 +291,18 @@ class Problem:
         buf = C.create_string_buffer(id_bytes, 128)
         _chk(lib().aar_comm_init(self.h, buf), "aar_comm_init")
 
+    def stats(self):
+        v = (C.c_int64 * 8)()
+        _chk(lib().aar_problem_stats(self.h, v), "aar_problem_stats")
+        return dict(zip(["slots", "pairs", "mruns", "schur_fma", "asm_jobs", "max_slots_per_frame", "frame_begin", "frame_end"], [int(x) for x in v]))
+
     def set_profiling(self, on=True):
         _chk(lib().aar_set_profiling(self.h, C.c_int32(int(on))), "aar_set_profiling")
 
     def phase_ms(self):
-        v = (C.c_double * 8)()
+        v = (C.c_double * 12)()
         _chk(lib().aar_get_phase_ms(self.h, v), "aar_get_phase_ms")
-        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm", "jacobian_kernel", "jacobian_launches", "accumulate_kernel"], list(v)))
+        return dict(zip(["jacobian", "schur_solve", "backsub", "residual", "decide_comm", "jacobian_kernel", "jacobian_launches", "accumulate_kernel", "syrk_kernel", "syrk_launches", "asm_pairs_kernel", "asm_mruns_kernel"], list(v)))
 
 
 def comm_unique_id() -> bytes:

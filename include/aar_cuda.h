@@ -144,6 +144,12 @@ int aar_lm_end(aar_problem *p, double *z_out);
  * per-frame 6-dof LM against the fixed rig, Jacobian by central differences on z
  * (calcDerivates, sparselevmarq.h:164-220).  z6 [num_frames_local][6] in/out. */
 int aar_track_batch(aar_problem *p, double *z6_inout, const aar_lm_params *params, double *final_cost, int32_t *iterations);
+/* the same in three steps — start poses to the device / all per-frame solves from the uploaded poses (repeatable) / results back —
+ * so that a caller can keep the poses resident; aar_track_ms: device time of the solves since aar_set_profiling(p, 1) */
+int aar_track_upload(aar_problem *p, const double *z6);
+int aar_track_run(aar_problem *p, const aar_lm_params *params);
+int aar_track_download(aar_problem *p, double *z6, double *final_cost, int32_t *iterations);
+int aar_track_ms(const aar_problem *p, double *ms, int64_t *runs);
 
 /* The frame shard a handle created from `desc` (rank, world_size) would own, computed on the host without touching a
  * device: contiguous frame-index range [frame_begin, frame_end) balanced by observation count, and its observation
@@ -164,9 +170,13 @@ int aar_comm_init(aar_problem *p, const void *id128);
  * the handle's stream) accumulated per phase since aar_set_profiling(p, 1):
  *   [0] expansion + Jacobian/normal-equation assembly  [1] Schur + all-reduce + reduced solve  [2] back-substitution
  *   [3] trial residual  [4] cost all-reduce + decision  [5] k_jac_project alone  [6] number of launches in [5]
- *   [7] k_jac_accumulate alone */
-#define AAR_NUM_PHASES 8
+ *   [7] the assembly kernels (k_asm_pairs + k_asm_mruns) alone  [8] k_schur_syrk alone  [9] number of launches in [8]
+ *   [10] k_asm_pairs alone  [11] k_asm_mruns alone */
+#define AAR_NUM_PHASES 12
 int64_t aar_kernel_launches(const aar_problem *p);
+/* sizes of this rank's shard: [0] W slots  [1] (frame, camera) pairs  [2] (frame, marker) runs  [3] fused multiply-adds of the upper
+ * triangle of the Schur update S -= E E^T per try  [4] assembly jobs  [5] most blocks seen by one frame  [6] [7] frame index range */
+int aar_problem_stats(const aar_problem *p, int64_t *out /* [8] */);
 int aar_set_profiling(aar_problem *p, int32_t on);
 int aar_get_phase_ms(const aar_problem *p, double *ms /* [AAR_NUM_PHASES] */);
 

@@ -1092,5 +1092,7 @@ double aar_oracle_time_ref_steps(OracleHandle *h, const double *z0, int iters) {
 #endif
 
 int aar_oracle_omp_threads(void) { return omp_get_max_threads(); }
+/* torch.distributed.run exports OMP_NUM_THREADS=1: the reference arm of bench.py sets its thread count itself */
+void aar_oracle_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 } /* extern "C" */

@@ -258,6 +258,29 @@ def test_full_size_properties_cfg3(binding, oracle_mod):
     assert abs(r_fin @ r_fin - fc) <= 1e-9 * fc
 
 
+def _track_against_reference(binding, oracle_mod, rig, with_huber, tol, label, frames=None):
+    p = binding.Problem(rig, cams=False, markers=False, objects=True, with_huber=with_huber)
+    z0 = p.mats2evec().reshape(-1, 6)
+    z_g, cost_g, it_g = p.track_batch(z0)
+    o = oracle_mod.Oracle(rig); o.set_config(cams=False, markers=False, objects=True, with_huber=with_huber)
+    worst_c = worst_z = 0.0; dit = 0
+    ks = range(len(rig.frame_ids)) if frames is None else frames
+    for k in ks:
+        fid = rig.frame_ids[k]
+        sel = rig.det_frame == fid
+        rows, z_init = o.track_init(fid, rig.T_frame_init[k], rig.det_cam[sel], rig.det_marker[sel], rig.det_xy[sel])
+        assert rows == 8 * sel.sum() and np.abs(z_init - z0[k]).max() < 1e-12
+        z_o, fc_o, it_o, _ = o.track_ref(z_init)
+        assert abs(int(it_g[k]) - it_o) <= 1, (k, it_g[k], it_o)
+        dit = max(dit, abs(int(it_g[k]) - it_o))
+        dc = abs(cost_g[k] - fc_o) / max(fc_o, 1e-12); dz = np.abs(z_g[k] - z_o).max() / max(1.0, np.abs(z_o).max())
+        worst_c = max(worst_c, dc); worst_z = max(worst_z, dz)
+        assert dc <= tol, (k, cost_g[k], fc_o)
+        assert dz <= tol, k
+    parity_record(label, frames_checked=len(list(ks)), observations=int(p.num_obs), worst_rel_dev_cost=worst_c, worst_rel_dev_z=worst_z, worst_iteration_count_diff=dit, bar=tol)
+    return z_g, cost_g, it_g, p
+
+
 @pytest.mark.parametrize("with_huber", [False, True])
 def test_track_batch_matches_reference_per_frame(binding, oracle_mod, with_huber):
     """MultiCamMapper::track() (mcm.cpp:430-443) batched over frames vs the oracle running the reference
@@ -267,21 +290,25 @@ def test_track_batch_matches_reference_per_frame(binding, oracle_mod, with_huber
     rig.T_cam_init, rig.T_marker_init = rig.T_cam_true, rig.T_marker_true          # the solved rig is fixed while tracking
     if with_huber:
         rig.det_xy = rig.det_xy.copy(); rig.det_xy[::23] += 12.0
-    p = binding.Problem(rig, cams=False, markers=False, objects=True, with_huber=with_huber)
-    z0 = p.mats2evec().reshape(-1, 6)
-    z_g, cost_g, it_g = p.track_batch(z0)
-    o = oracle_mod.Oracle(rig); o.set_config(cams=False, markers=False, objects=True, with_huber=with_huber)
-    for k, fid in enumerate(rig.frame_ids):
-        sel = rig.det_frame == fid
-        rows, z_init = o.track_init(fid, rig.T_frame_init[k], rig.det_cam[sel], rig.det_marker[sel], rig.det_xy[sel])
-        assert rows == 8 * sel.sum() and np.abs(z_init - z0[k]).max() < 1e-12
-        z_o, fc_o, it_o, _ = o.track_ref(z_init)
-        assert abs(int(it_g[k]) - it_o) <= 1, (k, it_g[k], it_o)
-        # north star: final cost and poses within 1e-6 relative.  With outliers + Huber the |d| <= 1e-4 pruning of
-        # calcDerivates (a discontinuity) and the early stop rule leave the reference itself reproducible to ~1e-5 only.
-        tol = 1e-5 if with_huber else 1e-6
-        assert abs(cost_g[k] - fc_o) <= tol * max(fc_o, 1e-12), (k, cost_g[k], fc_o)
-        assert np.abs(z_g[k] - z_o).max() <= tol * max(1.0, np.abs(z_o).max()), k
+    # north star: final cost and poses within 1e-6 relative.  With outliers + Huber the |d| <= 1e-4 pruning of
+    # calcDerivates (a discontinuity) and the early stop rule leave the reference itself reproducible to ~1e-5 only.
+    _track_against_reference(binding, oracle_mod, rig, with_huber, 1e-5 if with_huber else 1e-6, "track_small_rig_huber" if with_huber else "track_small_rig")
+
+
+def test_track_batch_at_cfg5_density(binding, oracle_mod, monkeypatch):
+    """BASELINE config 5 density (16 cameras, 64 markers, ~256 marker observations = 2 048 residual rows per frame), 240 frames:
+    every frame against the reference's 2-argument SparseLevMarq::solve, and the CTA-per-frame kernel against the
+    warp-per-frame kernel of round 1 (same arithmetic per residual, different summation order)."""
+    rig = copy.copy(synth.make_config("cfg5", frames=240))
+    rig.T_cam_init, rig.T_marker_init = rig.T_cam_true, rig.T_marker_true
+    z_g, cost_g, it_g, p = _track_against_reference(binding, oracle_mod, rig, False, 1e-6, "track_cfg5_density_240_frames")
+    monkeypatch.setenv("AAR_TRACK", "warp")
+    z_w, cost_w, it_w = p.track_batch(p.mats2evec().reshape(-1, 6))
+    monkeypatch.delenv("AAR_TRACK")
+    assert np.array_equal(it_w, it_g)
+    dz = np.abs(z_w - z_g).max(); dc = (np.abs(cost_w - cost_g) / cost_g).max()
+    parity_record("track_cta_kernel_vs_warp_kernel_cfg5_density", max_abs_dev_z=dz, max_rel_dev_cost=dc)
+    assert dz <= 1e-9 and dc <= 1e-9
 
 
 def test_edge_cases_ragged_inputs(binding, oracle_mod):

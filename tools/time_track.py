@@ -12,7 +12,10 @@ p = binding.Problem(rig, cams=False, markers=False, objects=True)
 z0 = p.mats2evec().reshape(-1, 6)
 p.track_batch(z0)                                   # warm-up
 t = time.time(); z, cost, its = p.track_batch(z0); dt = time.time() - t
-err = np.abs(np.array([synth.rodrigues(z[:, :3])[i] @ np.zeros(3) for i in range(1)])).sum()
+p.track_upload(z0); p.set_profiling(True)
+for _ in range(3): p.track_run()
+ms, runs = p.track_ms()
+print(f"device time of the solves alone: {ms / runs:.2f} ms per pass ({os.environ.get('AAR_TRACK', 'cta')} kernel)")
 print(f"{a.workload}: {rig.F} frames, {p.num_obs} observations: {dt * 1e3:.1f} ms -> {rig.F / dt:.0f} frames/s, {4 * p.num_obs / dt / 1e9:.3f} G corner-obs/s per solve; "
       f"iterations mean {its.mean():.1f} max {its.max()}, rms {np.sqrt(cost.sum() / (8 * p.num_obs)):.3f} px, "
       f"translation error max {np.abs(z[:, 3:] - rig.T_frame_true[:, :3, 3]).max():.2e} m")
