@@ -383,6 +383,8 @@ int push_state(aar_problem *p) {
 extern "C" {
 
 const char *aar_last_error(void) { return g_err.c_str(); }
+/* other translation units of the library (aar_init.cu) report through the same thread-local message */
+void aar_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 
 void aar_lm_default_params(aar_lm_params *q) {
     q->max_iters = 10000; q->min_error = 1e-5; q->min_step_error_diff = 0; q->min_average_step_error_diff = 1e-4;

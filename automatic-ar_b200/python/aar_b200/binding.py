@@ -35,11 +35,10 @@ class AarError(RuntimeError):
 
 def build(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_ROOT, "include", "aar_cuda.h"),
-                                                                 os.path.join(REPO_ROOT, "include", "aar_crsincos.h")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_ROOT, "include", f) for f in os.listdir(os.path.join(REPO_ROOT, "include"))]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "aar_cuda.cu")]
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "aar_cuda.cu"), os.path.join(CSRC, "aar_init.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         print(" ".join(cmd)); print(r.stdout); print(r.stderr)
@@ -309,3 +308,101 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _chk(lib().aar_comm_unique_id(buf), "aar_comm_unique_id")
     return buf.raw
+
+
+# ------------------------------------------------------------------ include/aar_init.h
+INIT_EXPORTS = ["aar_init_create", "aar_init_destroy", "aar_init_get_estimations", "aar_init_transforms", "aar_init_set_rig", "aar_init_object_transforms",
+                "aar_init_counts", "aar_init_get_ids", "aar_init_get_rig", "aar_init_get_object_transforms", "aar_init_edges", "aar_init_consensus", "aar_init_timings"]
+
+
+class InitDesc(C.Structure):
+    _fields_ = [("num_cams", C.c_int32), ("cam_K", C.c_void_p), ("cam_dist", C.c_void_p), ("marker_size", C.c_double), ("num_frames", C.c_int32),
+                ("num_detections", C.c_int64), ("det_frame", C.c_void_p), ("det_cam", C.c_void_p), ("det_marker", C.c_void_p), ("det_xy", C.c_void_p),
+                ("excluded_cams", C.c_void_p), ("threshold", C.c_double), ("min_detections", C.c_int32), ("consensus_max", C.c_int32),
+                ("device", C.c_int32), ("stream", C.c_void_p)]
+
+
+class Initializer:
+    """Initializer-shaped handle (include/aar_init.h): IPPE per detection, rig and object-pose initialisation on the device."""
+
+    def __init__(self, num_cams, K, dist, marker_size, num_frames, det_frame, det_cam, det_marker, det_xy, excluded=None, threshold=2.0,
+                 consensus_max=0, device=0, stream=None):
+        self.L = lib(); self.h = C.c_void_p()
+        self.N = len(det_frame)
+        self._keep = [np.ascontiguousarray(K, dtype=np.float64).reshape(num_cams, 9), np.ascontiguousarray(dist, dtype=np.float64).reshape(num_cams, 5),
+                      np.ascontiguousarray(det_frame, dtype=np.int32), np.ascontiguousarray(det_cam, dtype=np.int32),
+                      np.ascontiguousarray(det_marker, dtype=np.int32), np.ascontiguousarray(det_xy, dtype=np.float32).reshape(-1, 8)]
+        ex = np.zeros(num_cams, dtype=np.uint8)
+        if excluded is not None:
+            ex[list(excluded)] = 1
+        self._keep.append(ex)
+        k = self._keep
+        d = InitDesc(num_cams, _vp(k[0]), _vp(k[1]), float(marker_size), int(num_frames), self.N, _vp(k[2]), _vp(k[3]), _vp(k[4]), _vp(k[5]), _vp(ex),
+                     float(threshold), 2, int(consensus_max), int(device), stream)
+        _chk(self.L.aar_init_create(C.byref(d), C.byref(self.h)), "aar_init_create")
+
+    @classmethod
+    def from_rig(cls, rig, **kw):
+        nF = int(rig.frame_ids.max()) + 1 if rig.F else 0
+        return cls(rig.C, rig.K, rig.dist, float(rig.marker_size), nF, rig.det_frame, rig.det_cam, rig.det_marker, rig.det_xy, **kw)
+
+    def close(self):
+        if self.h:
+            self.L.aar_init_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def estimations(self):
+        T = np.zeros((self.N, 2, 4, 4)); err = np.zeros((self.N, 2)); nc = np.zeros(self.N, dtype=np.uint8)
+        _chk(self.L.aar_init_get_estimations(self.h, _vp(T), _vp(err), _vp(nc)), "aar_init_get_estimations")
+        return T, err, nc
+
+    def init_transforms(self):
+        _chk(self.L.aar_init_transforms(self.h), "aar_init_transforms")
+
+    def set_rig(self, cam_ids, cam_T, marker_ids, marker_T):
+        ci = np.ascontiguousarray(cam_ids, dtype=np.int32); mi = np.ascontiguousarray(marker_ids, dtype=np.int32)
+        cT = np.ascontiguousarray(cam_T, dtype=np.float64); mT = np.ascontiguousarray(marker_T, dtype=np.float64)
+        _chk(self.L.aar_init_set_rig(self.h, len(ci), _vp(ci), _vp(cT), len(mi), _vp(mi), _vp(mT)), "aar_init_set_rig")
+
+    def init_object_transforms(self):
+        _chk(self.L.aar_init_object_transforms(self.h), "aar_init_object_transforms")
+
+    def counts(self):
+        c = np.zeros(7, dtype=np.int32)
+        _chk(self.L.aar_init_counts(self.h, _vp(c)), "aar_init_counts")
+        return c
+
+    def results(self):
+        c = self.counts()
+        cam_ids = np.zeros(c[0], dtype=np.int32); marker_ids = np.zeros(c[1], dtype=np.int32)
+        _chk(self.L.aar_init_get_ids(self.h, _vp(cam_ids), _vp(marker_ids)), "aar_init_get_ids")
+        ci = np.zeros(c[2], dtype=np.int32); cT = np.zeros((c[2], 4, 4)); mi = np.zeros(c[3], dtype=np.int32); mT = np.zeros((c[3], 4, 4))
+        _chk(self.L.aar_init_get_rig(self.h, _vp(ci), _vp(cT), _vp(mi), _vp(mT)), "aar_init_get_rig")
+        fi = np.zeros(c[4], dtype=np.int32); fT = np.zeros((c[4], 4, 4))
+        _chk(self.L.aar_init_get_object_transforms(self.h, _vp(fi), _vp(fT)), "aar_init_get_object_transforms")
+        return dict(cam_ids=cam_ids, marker_ids=marker_ids, root_cam=int(c[5]), root_marker=int(c[6]), cams=(ci, cT), markers=(mi, mT), objects=(fi, fT))
+
+    def edges(self, cams=True):
+        n = C.c_int32(0)
+        _chk(self.L.aar_init_edges(self.h, int(cams), 0, None, None, None, None, C.byref(n)), "aar_init_edges")
+        a = np.zeros(n.value, dtype=np.int32); b = np.zeros(n.value, dtype=np.int32); ln = np.zeros(n.value, dtype=np.int64); w = np.zeros(n.value)
+        _chk(self.L.aar_init_edges(self.h, int(cams), n.value, _vp(a), _vp(b), _vp(ln), _vp(w), C.byref(n)), "aar_init_edges")
+        return a, b, ln, w
+
+    def timings(self):
+        ms = np.zeros(3); n = C.c_int64(0)
+        _chk(self.L.aar_init_timings(self.h, _vp(ms), C.byref(n)), "aar_init_timings")
+        return dict(ippe_ms=ms[0], rig_ms=ms[1], objects_ms=ms[2], launches=n.value)
+
+
+def init_consensus(marker_size, T, T1inv, T2inv, device=0):
+    """aar_init_consensus: (index of the winner, its consensus error)."""
+    T = np.ascontiguousarray(T, dtype=np.float64); A = np.ascontiguousarray(T1inv, dtype=np.float64); B = np.ascontiguousarray(T2inv, dtype=np.float64)
+    best = C.c_int32(-1); w = C.c_double(0)
+    _chk(lib().aar_init_consensus(int(device), C.c_double(marker_size), C.c_int64(len(T)), _vp(T), _vp(A), _vp(B), C.byref(best), C.byref(w)), "aar_init_consensus")
+    return best.value, w.value

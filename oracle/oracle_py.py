@@ -207,3 +207,102 @@ def undistort(xy, K, dist):
 def sincos(x):
     L, _ = load(); s = C.c_double(0); c = C.c_double(0)
     L.aar_oracle_sincos(C.c_double(x), C.byref(s), C.byref(c)); return s.value, c.value
+
+
+class InitOracle:
+    """The restated Initializer (oracle/init_oracle.cpp) on flat detections in aruco.detections order."""
+
+    def __init__(self, num_cams, K, dist, marker_size, num_frames, det_frame, det_cam, det_marker, det_xy, excluded=None,
+                 threshold=2.0, consensus_max=0, sincos_mode=1, prefer_ref=True):
+        self.L, _ = load(prefer_ref)
+        self.L.aar_oracle_set_sincos_mode(C.c_int(sincos_mode))
+        self.L.aar_init_oracle_create.restype = C.c_void_p
+        self.N = len(det_frame); self.num_cams = num_cams; self.num_frames = num_frames
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(num_cams, 9); dist = np.ascontiguousarray(dist, dtype=np.float64).reshape(num_cams, 5)
+        df = np.ascontiguousarray(det_frame, dtype=np.int32); dc = np.ascontiguousarray(det_cam, dtype=np.int32)
+        dm = np.ascontiguousarray(det_marker, dtype=np.int32); xy = np.ascontiguousarray(det_xy, dtype=np.float32).reshape(-1, 8)
+        ex = np.zeros(num_cams, dtype=np.uint8)
+        if excluded is not None:
+            ex[list(excluded)] = 1
+        self.h = C.c_void_p(self.L.aar_init_oracle_create(C.c_int(num_cams), _ptr(K, _dp), _ptr(dist, _dp), C.c_double(marker_size), C.c_int(num_frames),
+                                                          C.c_int64(self.N), _ptr(df, _ip), _ptr(dc, _ip), _ptr(dm, _ip), _ptr(xy, _fp),
+                                                          ex.ctypes.data_as(C.c_void_p), C.c_double(threshold), C.c_int(consensus_max)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.aar_init_oracle_destroy(self.h); self.h = None
+
+    def obtain_pose_estimations(self):
+        self.L.aar_init_oracle_obtain_pose_estimations(self.h)
+        T = np.zeros((self.N, 2, 4, 4)); err = np.zeros((self.N, 2)); nc = np.zeros(self.N, dtype=np.uint8)
+        self.L.aar_init_oracle_get_estimations(self.h, _ptr(T, _dp), _ptr(err, _dp), nc.ctypes.data_as(C.c_void_p))
+        return T, err, nc
+
+    def init_transforms(self):
+        self.L.aar_init_oracle_init_transforms(self.h)
+
+    def init_object_transforms(self):
+        self.L.aar_init_oracle_init_object_transforms(self.h)
+
+    def set_rig(self, cam_ids, cam_T, marker_ids, marker_T):
+        ci = np.ascontiguousarray(cam_ids, dtype=np.int32); mi = np.ascontiguousarray(marker_ids, dtype=np.int32)
+        cT = np.ascontiguousarray(cam_T, dtype=np.float64); mT = np.ascontiguousarray(marker_T, dtype=np.float64)
+        self.L.aar_init_oracle_set_rig(self.h, C.c_int(len(ci)), _ptr(ci, _ip), _ptr(cT, _dp), C.c_int(len(mi)), _ptr(mi, _ip), _ptr(mT, _dp))
+
+    def _map(self, fn):
+        n = fn(self.h, C.c_int(0), None, None)
+        ids = np.zeros(n, dtype=np.int32); T = np.zeros((n, 4, 4))
+        fn(self.h, C.c_int(n), _ptr(ids, _ip), _ptr(T, _dp))
+        return ids, T
+
+    def _set(self, fn):
+        n = fn(self.h, C.c_int(0), None)
+        ids = np.zeros(n, dtype=np.int32)
+        fn(self.h, C.c_int(n), _ptr(ids, _ip))
+        return ids
+
+    def results(self):
+        L = self.L
+        return dict(cam_ids=self._set(L.aar_init_oracle_cam_ids), marker_ids=self._set(L.aar_init_oracle_marker_ids),
+                    root_cam=int(L.aar_init_oracle_root_cam(self.h)), root_marker=int(L.aar_init_oracle_root_marker(self.h)),
+                    cams=self._map(L.aar_init_oracle_transforms_to_root_cam), markers=self._map(L.aar_init_oracle_transforms_to_root_marker),
+                    objects=self._map(L.aar_init_oracle_object_transforms))
+
+    def edges(self, cams=True):
+        n = self.L.aar_init_oracle_edges(self.h, C.c_int(int(cams)), C.c_int(0), None, None, None, None)
+        a = np.zeros(n, dtype=np.int32); b = np.zeros(n, dtype=np.int32); ln = np.zeros(n, dtype=np.int64); w = np.zeros(n)
+        self.L.aar_init_oracle_edges(self.h, C.c_int(int(cams)), C.c_int(n), _ptr(a, _ip), _ptr(b, _ip), _ptr(ln, _lp), _ptr(w, _dp))
+        return a, b, ln, w
+
+
+def init_solve_pnp(size, raw8, K, dist, sincos_mode=1):
+    """aruco::solvePnP_ of one detection: (T [2,4,4] float32-valued, err [2])."""
+    L, _ = load()
+    L.aar_oracle_set_sincos_mode(C.c_int(sincos_mode))
+    raw = np.ascontiguousarray(raw8, dtype=np.float32); K = np.ascontiguousarray(K, dtype=np.float64); d = np.ascontiguousarray(dist, dtype=np.float64)
+    T = np.zeros((2, 4, 4)); e = np.zeros(2)
+    L.aar_init_oracle_solve_pnp(C.c_float(size), _ptr(raw, _fp), _ptr(K, _dp), _ptr(d, _dp), _ptr(T, _dp), _ptr(e, _dp))
+    return T, e
+
+
+def init_ippe_raw(size, raw8, K, dist):
+    """intermediate values of solvePoseOfCentredSquare: normalised points, H, (Ra, ta), (Rb, tb), float errors."""
+    L, _ = load()
+    raw = np.ascontiguousarray(raw8, dtype=np.float32); K = np.ascontiguousarray(K, dtype=np.float64); d = np.ascontiguousarray(dist, dtype=np.float64)
+    q = np.zeros(8, dtype=np.float32); H = np.zeros(9); Ra = np.zeros(9); ta = np.zeros(3); Rb = np.zeros(9); tb = np.zeros(3); er = np.zeros(2, dtype=np.float32)
+    L.aar_init_oracle_ippe_raw(C.c_float(size), _ptr(raw, _fp), _ptr(K, _dp), _ptr(d, _dp), _ptr(q, _fp), _ptr(H, _dp), _ptr(Ra, _dp), _ptr(ta, _dp), _ptr(Rb, _dp), _ptr(tb, _dp), _ptr(er, _fp))
+    return q, H.reshape(3, 3), Ra.reshape(3, 3), ta, Rb.reshape(3, 3), tb, er
+
+
+def init_consensus(marker_size, T, T1inv, T2inv, consensus_max=0):
+    L, _ = load()
+    T = np.ascontiguousarray(T, dtype=np.float64); A = np.ascontiguousarray(T1inv, dtype=np.float64); B = np.ascontiguousarray(T2inv, dtype=np.float64)
+    w = C.c_double(0)
+    i = L.aar_init_oracle_consensus(C.c_double(marker_size), C.c_int64(len(T)), _ptr(T, _dp), _ptr(A, _dp), _ptr(B, _dp), C.c_int(consensus_max), C.byref(w))
+    return int(i), w.value
+
+
+def acos_shared(x):
+    L, _ = load()
+    L.aar_init_oracle_acos.restype = C.c_double
+    return L.aar_init_oracle_acos(C.c_double(x))

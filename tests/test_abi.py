@@ -23,6 +23,12 @@ def test_library_exports_every_declared_symbol(binding):
     L = C.CDLL(binding.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
+    # the initialisation path (include/aar_init.h)
+    hdr = open(os.path.join(ROOT, "include", "aar_init.h")).read()
+    declared = set(re.findall(r"\b(aar_init_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(binding.INIT_EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
 
 
 def test_struct_layouts_match_header(binding):
@@ -31,6 +37,7 @@ def test_struct_layouts_match_header(binding):
     assert C.sizeof(binding.LmTrace) == 40
     assert C.sizeof(binding.LmReport) == 48
     assert C.sizeof(binding.Desc) == 176
+    assert C.sizeof(binding.InitDesc) == 120
 
 
 def test_no_cpu_fallback_without_device(binding):
@@ -41,6 +48,11 @@ def test_no_cpu_fallback_without_device(binding):
     rig = synth.make_rig(C=2, M=3, F=5, obs_per_frame=4.0, seed=1)
     with pytest.raises(binding.AarError, match="CUDA"):
         binding.Problem(rig)
+    with pytest.raises(binding.AarError, match="CUDA"):
+        binding.Initializer.from_rig(rig)
+    with pytest.raises(binding.AarError, match="CUDA"):
+        import numpy as np
+        binding.init_consensus(0.05, np.eye(4)[None], np.eye(4)[None], np.eye(4)[None])
 
 
 def test_product_does_not_reference_the_oracle():
@@ -49,4 +61,4 @@ def test_product_does_not_reference_the_oracle():
         for f in files:
             if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
-                assert "oracle_py" not in src and "libaar_oracle" not in src and "mcm_oracle" not in src, f
+                assert "oracle_py" not in src and "libaar_oracle" not in src and "mcm_oracle" not in src and "init_oracle" not in src, f
