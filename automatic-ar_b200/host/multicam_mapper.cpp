@@ -1,5 +1,6 @@
 // multicam_mapper.cpp — see multicam_mapper.h.  Reference line numbers are into /root/reference/libs/multicam_mapper.cpp.
 #include "multicam_mapper.h"
+#include "initializer.h"
 
 #include <algorithm>
 #include <cmath>
@@ -96,6 +97,10 @@ std::vector<CamConfig> CamConfig::read_cam_configs(const std::string &folder) {
 
 // ------------------------------------------------------------------------------- MultiCamMapper
 MultiCamMapper::MultiCamMapper() {}
+MultiCamMapper::MultiCamMapper(Initializer &in) {                            // :252-254
+    init((size_t)in.get_root_cam(), in.get_transforms_to_root_cam(), (size_t)in.get_root_marker(), in.get_transforms_to_root_marker(), in.get_object_transforms(),
+         in.get_frame_cam_markers(), (float)in.get_marker_size(), in.get_cam_configs());
+}
 MultiCamMapper::MultiCamMapper(size_t root_c, const std::map<int, Mat44> &Tc, size_t root_m, const std::map<int, Mat44> &Tm, const std::map<int, Mat44> &To,
                                const FrameCamMarkers &fcm, float m_size, const std::vector<CamConfig> &cc) { init(root_c, Tc, root_m, Tm, To, fcm, m_size, cc); }
 MultiCamMapper::~MultiCamMapper() { drop_handle(); }
@@ -118,7 +123,7 @@ void MultiCamMapper::init(size_t root_c, const std::map<int, Mat44> &Tc, size_t 
                           const FrameCamMarkers &fcm, float m_size, const std::vector<CamConfig> &cc) {
     drop_handle();
     root_cam = root_c; root_marker = root_m; marker_size = m_size;
-    transforms_to_root_cam = Tc; transforms_to_root_marker = Tm; object_to_global = To; frame_cam_markers = fcm;
+    transforms_to_root_cam = Tc; transforms_to_root_marker = Tm; object_to_global = To; frame_cam_markers = fcm; raw_frame_cam_markers = fcm;
     cam_configs.clear();
     for (auto &p : transforms_to_root_cam) {                     // cam_mats[i] = cam_confs[cam_id] (:314-316)
         if (p.first < 0 || (size_t)p.first >= cc.size()) throw std::runtime_error("no CamConfig for camera " + std::to_string(p.first));
@@ -136,7 +141,7 @@ void MultiCamMapper::init(size_t root_c, const std::map<int, Mat44> &Tc, size_t 
 
 void MultiCamMapper::init(const std::map<int, Mat44> &object_poses, const FrameCamMarkers &fcm) {
     drop_handle();
-    object_to_global = object_poses; frame_cam_markers = fcm;
+    object_to_global = object_poses; frame_cam_markers = fcm; raw_frame_cam_markers = fcm;
     corners_undistorted = false;
     Config keep = config; config.optimize_cam_intrinsics = false;
     make_handle(false);
@@ -153,7 +158,12 @@ void MultiCamMapper::make_handle(bool undist) {
     for (auto &p : transforms_to_root_cam) { cam_ids.push_back(p.first); Tc.insert(Tc.end(), p.second.m, p.second.m + 16); const CamConfig &c = cam_configs.at(p.first); K.insert(K.end(), c.K, c.K + 9); D.insert(D.end(), c.dist, c.dist + 5); }
     for (auto &p : transforms_to_root_marker) { marker_ids.push_back(p.first); Tm.insert(Tm.end(), p.second.m, p.second.m + 16); }
     for (auto &p : object_to_global) { frame_ids.push_back(p.first); To.insert(To.end(), p.second.m, p.second.m + 16); }
-    for (auto &f : frame_cam_markers)
+    // The reference's inverted indices keep the RAW corners (fill_iteration_arrays :304 runs before remove_distortions :322) and its
+    // Jacobian differences them (obtain_marker_derivs :981-989): whenever this object was initialised from raw detections the handle
+    // is rebuilt from them (the device undistorts again, deterministically); only a .solution file has nothing but undistorted corners.
+    const bool from_raw = !raw_frame_cam_markers.empty();
+    if (from_raw) undist = false;
+    for (auto &f : (from_raw ? raw_frame_cam_markers : frame_cam_markers))
         for (auto &c : f.second)
             for (auto &mk : c.second) { df.push_back(f.first); dc.push_back(c.first); dm.push_back(mk.id); xy.insert(xy.end(), mk.xy, mk.xy + 8); }
     aar_problem_desc d; std::memset(&d, 0, sizeof d);
@@ -289,7 +299,7 @@ bool MultiCamMapper::read_solution_file(const std::string &path) {
     std::ifstream f(path, std::ios_base::binary);
     if (!f.is_open()) { std::cout << "Could not open a file in: " << path << " for reading." << std::endl; return false; }
     drop_handle();
-    transforms_to_root_cam.clear(); transforms_to_root_marker.clear(); object_to_global.clear(); cam_configs.clear(); frame_cam_markers.clear();
+    transforms_to_root_cam.clear(); transforms_to_root_marker.clear(); object_to_global.clear(); cam_configs.clear(); frame_cam_markers.clear(); raw_frame_cam_markers.clear();
     size_t C = 0, M = 0, F = 0;
     if (!rd(f, C)) return false;
     std::vector<int> cid(C); for (auto &v : cid) rd(f, v);

@@ -1,7 +1,7 @@
 // multicam_mapper.h — host-side mirror of the reference's MultiCamMapper (/root/reference/libs/multicam_mapper.h:14-83)
 // for the joint-optimisation path: same method names, argument meaning and file formats, cv::Mat replaced by
 // aar::Mat44, the optimisation itself forwarded to the CUDA path through the C ABI of include/aar_cuda.h.
-// What is NOT here: the Initializer constructor, overlays / visualisation (GUI), stereo-calib and ground-truth files.
+// What is NOT here: overlays / visualisation (GUI), stereo-calib and ground-truth files.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -23,12 +23,15 @@ template <typename T> struct SparseLevMarq {
 
 namespace aar {
 
+class Initializer;
+
 class MultiCamMapper {
 public:
     struct Config {            // multicam_mapper.h:75-81
         bool optimize_cam_poses = true, optimize_object_poses = true, optimize_marker_poses = true, optimize_cam_intrinsics = true;
     };
     MultiCamMapper();
+    explicit MultiCamMapper(Initializer &initializer);                     // multicam_mapper.cpp:252-254
     MultiCamMapper(size_t root_c, const std::map<int, Mat44> &T_to_root_cam, size_t root_m, const std::map<int, Mat44> &T_to_root_marker,
                    const std::map<int, Mat44> &obj_transforms, const FrameCamMarkers &fcm, float m_size, const std::vector<CamConfig> &cam_confs);
     ~MultiCamMapper();
@@ -72,6 +75,7 @@ public:
     std::map<int, Mat44> transforms_to_root_cam, transforms_to_root_marker, object_to_global;
     std::map<int, CamConfig> cam_configs;
     FrameCamMarkers frame_cam_markers;                          // undistorted after init(), like the reference
+    FrameCamMarkers raw_frame_cam_markers;                      // what init() received (empty after read_solution_file): the Jacobian's corners
 
 private:
     void mats2eVec(const Config &conf, std::vector<double> &out) const;       // :445-461, R -> r like cv::Rodrigues

@@ -1,9 +1,11 @@
 // solution_tool — format round trips for the tests (no GPU needed):
 //   solution_tool roundtrip <in.solution> <out.solution> [<out.yaml>]     read + write back (must be byte identical)
 //   solution_tool detections <in.detections> <out.detections>             read + write back
+//   solution_tool calib <data_folder> -                                   CamConfig::read_cam_configs: one line per camera, %.17g
 //   solution_tool resolve <in.solution> <out.solution>                    (GPU) re-create the mapper through the 8-argument
 //                         init() — the Initializer-output path: raw corners, device undistortion — and solve()
 #include <algorithm>
+#include <cstdio>
 #include <iostream>
 #include "multicam_mapper.h"
 int main(int argc, char **argv) {
@@ -19,6 +21,14 @@ int main(int argc, char **argv) {
             auto d = aar::MultiCamMapper::read_detections_file(argv[2]);
             aar::MultiCamMapper::write_detections_file(argv[3], d);
             std::cout << d.size() << " frames" << std::endl;
+        } else if (mode == "calib") {
+            const std::vector<aar::CamConfig> cc = aar::CamConfig::read_cam_configs(argv[2]);
+            for (const aar::CamConfig &c : cc) {
+                std::printf("%d %d", c.width, c.height);
+                for (int i = 0; i < 9; i++) std::printf(" %.17g", c.K[i]);
+                for (int i = 0; i < 5; i++) std::printf(" %.17g", c.dist[i]);
+                std::printf("\n");
+            }
         } else if (mode == "resolve") {
             aar::MultiCamMapper in;
             if (!in.read_solution_file(argv[2])) return 1;
