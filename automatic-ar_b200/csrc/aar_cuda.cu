@@ -345,12 +345,12 @@ int build_and_solve_reduced(aar_problem *p) {
         bool done = false;
         if (nblk <= 16 && p->use_cluster_solve) {
             // one thread-block cluster, the factor lives in distributed shared memory (aar_dense.cuh)
-            const size_t smem = ((size_t)CH_NB * (nblk * CH_NB + 2) + 3 * CH_NB * CH_LD + (size_t)nblk * CH_NB + CH_NB) * sizeof(double);
+            const size_t smem = cluster2_smem_bytes(nblk);
             cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = p->stream;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            const double *Sc = S, *bc = b; const LmState *stp = p->d_st.p;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduced_solve_cluster, n_r, Sc, bc, p->d_dr.p, stp, p->d_flag.p);
+            const double *bc = b; const LmState *stp = p->d_st.p;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduced_solve_cluster2, n_r, S, bc, p->d_dr.p, stp, p->d_flag.p, p->d_xinv.p);
             if (e == cudaSuccess) { done = true; p->launches++; }
             else { cudaGetLastError(); p->use_cluster_solve = false; }      // e.g. the cluster cannot be scheduled: fall back for good
         }
@@ -686,11 +686,11 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     CU(cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     {   // cluster Cholesky: up to 16 CTAs per cluster (non-portable size), block row + staging in shared memory
         const int nblk = (p->n_r + CH_NB - 1) / CH_NB;
-        const size_t smem = ((size_t)CH_NB * (nblk * CH_NB + 2) + 3 * CH_NB * CH_LD + (size_t)nblk * CH_NB + CH_NB) * sizeof(double);
-        const char *e = getenv("AAR_NO_CLUSTER_SOLVE");
-        if (nblk > 16 || smem > p->smem_optin - 1024 || (e && *e == '1')) p->use_cluster_solve = false;
-        else if (cudaFuncSetAttribute(k_reduced_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                 cudaFuncSetAttribute(k_reduced_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); p->use_cluster_solve = false; }
+        const size_t smem = cluster2_smem_bytes(nblk);
+        const char *e = getenv("AAR_NO_CLUSTER_SOLVE");                       // development aid: force the cooperative-grid kernel
+        if (nblk > 16 || smem > p->smem_optin - 1024 || (p->n_r & 1) || (e && *e == '1')) p->use_cluster_solve = false;
+        else if (cudaFuncSetAttribute(k_reduced_solve_cluster2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                 cudaFuncSetAttribute(k_reduced_solve_cluster2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); p->use_cluster_solve = false; }
     }
     if ((size_t)p->n_r * sizeof(double) > 48 * 1024) CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)p->n_r * sizeof(double))));
     CU(cudaStreamSynchronize(p->stream));

@@ -77,7 +77,7 @@ int main(int argc, char **argv) {
         auto start = std::chrono::system_clock::now();
         mcm.solve();
         d += std::chrono::system_clock::now() - start;
-        std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
+        std::cout.precision(17); std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
         mcm.write_solution_file(final_path);
         mcm.write_text_solution_file(final_path + ".yaml");
         const int minutes = (int)(d.count() / 60); const long seconds = std::lround(d.count() - minutes * 60);

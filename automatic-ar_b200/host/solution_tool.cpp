@@ -39,7 +39,7 @@ int main(int argc, char **argv) {
                                     in.frame_cam_markers, (float)in.get_marker_size(), confs);
             mcm.set_optmize_flag_cam_intrinsics(false);
             mcm.solve();
-            std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
+            std::cout.precision(17); std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
             if (!mcm.write_solution_file(argv[3])) return 1;
         } else return -1;
     } catch (const std::exception &e) { std::cerr << e.what() << std::endl; return 2; }
