@@ -87,8 +87,10 @@ struct aar_problem {
     std::vector<int> g_frame, g_cam, g_marker, g_hasjac; // indices per global observation
     int f_begin = 0, f_end = 0;                    // this rank's frame index range
     long long o_begin = 0, o_end = 0;              // this rank's observation range
-    int nrc = 0, nrm = 0, n_r = 0;
-    long long n_vars = 0;
+    int nrc = 0, nrm = 0, nri = 0, n_r = 0; bool opt_i = false;   // nri: 2 C intrinsics pseudo-blocks (aar_intrinsics.cuh)
+    long long n_vars = 0;        // INTERNAL length of z: reduced part (pose blocks, then 12 per camera when the intrinsics are optimised), then frames
+    long long n_vars_ext = 0;    // length of the reference's io_vec (get_num_vars, multicam_mapper.cpp:239-250): ... frames, then 9 per camera
+    std::vector<double> z_stage; // host staging of the io_vec <-> internal conversion
     long long nslots = 0; int max_slots = 0;
     long long schur_fma = 0;                       // sum over local frames of 6 * n_f (n_f + 1) / 2, n_f = 6 * (blocks seen): the upper triangle of S -= E E^T
     // ---- device
@@ -101,6 +103,7 @@ struct aar_problem {
     bool legacy_acc = false;                                                          // AAR_ASM=legacy: round-1 lane-per-observation kernel (A/B aid)
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_z0, d_trk_cost; bool trk_have_z0 = false; double track_ms = 0; long long track_runs = 0;
     DevBuf<double> d_fc, d_E, d_xinv;
+    DevBuf<int> d_pair_slot_i; DevBuf<double> d_intr_tr, d_Ji;
     DevBuf<double> d_intr, d_K9, d_dist5, d_cam_tab, d_mk_tab, d_fr_tab, d_cam_tr, d_mk_tr, d_fr_tr, d_cam_fixed, d_mk_fixed, d_fr_fixed;
     DevBuf<double> d_z, d_zt, d_z0, d_Hf, d_W, d_Hrr, d_gr, d_red, d_dr, d_red3, d_tmp, d_r, d_J;
     DevBuf<LmState> d_st;
@@ -196,6 +199,7 @@ int allreduce(aar_problem *p, double *buf, size_t n, ncclRedOp_t op) {
 // residual sum of squares at dz into d_red3[0] (must be zeroed by the caller); optional residual vector
 int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_out) {
     LAUNCH(p, k_expand_trial, cdiv((long long)p->C + p->M + p->dp.F, 128), 128, 0, p->dp, dz);
+    if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, dz, p->d_intr_tr.p);
     if (p->dp.N > 0)
         LAUNCH(p, k_residual, cdiv(p->dp.N, 256), 256, 0, p->dp, p->d_cam_tr.p, POSE_STRIDE, p->d_mk_tr.p, POSE_STRIDE, p->d_fr_tr.p, POSE_STRIDE, huber_delta, d_r_out, p->d_red3.p);
     return AAR_OK;
@@ -215,6 +219,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
     prof_mark(p, 7);
     if (p->legacy_acc) {
+        if (p->opt_i) { set_err("AAR_ASM=legacy has no intrinsics block"); return AAR_ERR_UNSUPPORTED; }
         constexpr int AW = 8;
         auto k1 = k_jac_project<JT, false>; auto k2 = k_jac_accumulate<JT, AW>;
         const size_t scr = (size_t)AW * SCR_DOUBLES * sizeof(double), fix = (size_t)(p->nrc + p->nrm) * 27 * sizeof(double);
@@ -267,6 +272,11 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
         const int grid3 = (int)std::min<long long>((long long)std::max(per_sm, 1) * p->num_sms, want);
         LAUNCH(p, k3, grid3, ASM_THREADS, smem3, p->dp, pl, Jn, p->huber ? p->d_Rv.p : nullptr, p->d_W.p, p->d_Hrr.p, p->d_gr.p);
     }
+    if (p->opt_i && p->npairs > 0) {   // intrinsics columns (aar_intrinsics.cuh): one warp per (frame, camera) pair, from the same staged rows
+        auto k4 = k_intr_assemble<JT>;
+        LAUNCH(p, k4, cdiv((long long)p->npairs * 32, 128), 128, 0, p->dp, p->d_pair_info.p, p->d_pair_cam.p, p->d_pair_slot_i.p, Jn, p->huber ? p->d_Rv.p : nullptr, s1, s2,
+               p->d_W.p, p->d_Hrr.p, p->d_gr.p);
+    }
     prof_mark(p, 8);
     return AAR_OK;
 }
@@ -276,8 +286,13 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
 int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
+    if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, p->d_z.p, p->d_intr.p);
     if (p->npairs > 0) LAUNCH(p, k_pair_tab, cdiv((long long)p->npairs * PAIR_TAB, 256), 256, 0, p->dp);
-    if (Jdump) { if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump); return AAR_OK; }
+    if (Jdump) {
+        if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump);
+        if (p->opt_i && p->dp.N > 0) { if (p->d_Ji.n < 32 * (size_t)p->dp.N) CU(p->d_Ji.alloc(32 * (size_t)p->dp.N)); LAUNCH(p, k_intr_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, p->d_Ji.p); }
+        return AAR_OK;
+    }
     const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool exact = p->force_exact_staging || attempt == 1;
@@ -316,7 +331,7 @@ __global__ void k_prepare_reduced(int n_r, const double *__restrict__ Hrr, const
 
 // Schur elimination of the frame blocks of this rank into S (must hold Hrr) and b (must hold -gr)
 int schur_eliminate(aar_problem *p, double *S, double *b) {
-    const int n_r = p->n_r, nb = p->nrc + p->nrm, F = p->dp.F;
+    const int n_r = p->n_r, nb = p->nrc + p->nrm + p->nri, F = p->dp.F;
     if (!p->opt_f || F <= 0) return AAR_OK;
     LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);      // also feeds k_backsub
     if (n_r > 0 && p->nslots > 0) {
@@ -394,7 +409,6 @@ void aar_lm_default_params(aar_lm_params *q) {
 static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_only) {
     if (!d || !out) { set_err("null argument"); return AAR_ERR_INVALID; }
     *out = nullptr;
-    if (d->optimize_cam_intrinsics) { set_err("optimize_cam_intrinsics is not supported by the device path (SURVEY 8f row 4)"); return AAR_ERR_UNSUPPORTED; }
     if (d->num_cams < 1 || d->num_markers < 1 || d->num_frames < 0 || d->num_cams > 4095 || d->num_markers > 500000) { set_err("bad counts"); return AAR_ERR_INVALID; }
     aar_problem *p = new aar_problem();
     std::unique_ptr<aar_problem, void (*)(aar_problem *)> guard(p, aar_problem_destroy);
@@ -422,8 +436,10 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     p->J_delta = d->J_delta > 0 ? d->J_delta : 1e-3;
     p->device = d->device; p->rank = d->world_size > 1 ? d->rank : 0; p->world = d->world_size > 1 ? d->world_size : 1;
     if (p->rank < 0 || p->rank >= p->world) { set_err("bad rank"); return AAR_ERR_INVALID; }
-    p->nrc = p->opt_c ? p->C - 1 : 0; p->nrm = p->opt_m ? p->M - 1 : 0; p->n_r = 6 * (p->nrc + p->nrm);
+    p->opt_i = d->optimize_cam_intrinsics != 0;
+    p->nrc = p->opt_c ? p->C - 1 : 0; p->nrm = p->opt_m ? p->M - 1 : 0; p->nri = p->opt_i ? 2 * p->C : 0; p->n_r = 6 * (p->nrc + p->nrm + p->nri);
     p->n_vars = p->n_r + (p->opt_f ? 6LL * p->F : 0);
+    p->n_vars_ext = 6LL * (p->nrc + p->nrm) + (p->opt_f ? 6LL * p->F : 0) + (p->opt_i ? 9LL * p->C : 0);
 
     // ---- fill_iteration_arrays (multicam_mapper.cpp:345-377): frame id ^, cam id ^, detection order;
     // detections of unknown cameras / markers are erased.  (Detections of a frame without an object pose make
@@ -494,30 +510,31 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     // distinct active marker blocks; cs_cum / ms_cum are the running numbers of camera / marker slots.
     // Two passes over the local frames (count, prefix sum, fill), both parallel.
     if (Nl >= (1LL << 31) - 1) { set_err("more than 2^31 observations on one rank"); return AAR_ERR_UNSUPPORTED; }
-    const int nblk_r = p->nrc + p->nrm;
-    std::vector<int> slot_ptr((size_t)Fl + 1, 0), cs_cum((size_t)Fl + 1, 0), ms_cum((size_t)Fl + 1, 0), slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1);
-    const bool slots_c = p->opt_f && p->opt_c, slots_m = p->opt_f && p->opt_m;
+    const int nblk_r = p->nrc + p->nrm + p->nri;
+    std::vector<int> slot_ptr((size_t)Fl + 1, 0), cs_cum((size_t)Fl + 1, 0), ms_cum((size_t)Fl + 1, 0), is_cnt((size_t)Fl + 1, 0), slot_c((size_t)Nl, -1), slot_m((size_t)Nl, -1), slot_i((size_t)Nl, -1);
+    const bool slots_c = p->opt_f && p->opt_c, slots_m = p->opt_f && p->opt_m, slots_i = p->opt_f && p->opt_i;   // intrinsics: pseudo-block A of every camera seen, root included
     const int Tf = host_threads(Nl);
     parallel_for(Fl, Tf, [&](long long f0, long long f1, int) {
         std::vector<long long> stamp((size_t)std::max(nblk_r, 1), -1);
         for (long long f = f0; f < f1; f++) {
             const long long o0 = frame_ptr[(size_t)(p->f_begin + f)], o1 = frame_ptr[(size_t)(p->f_begin + f) + 1];
-            int ncs = 0, nms = 0;
+            int ncs = 0, nms = 0, nis = 0;
             for (long long o = o0; o < o1; o++) {
                 const int c = p->g_cam[(size_t)o], m = p->g_marker[(size_t)o];
                 if (slots_c && c != p->root_cam) { const size_t bk = (size_t)(c - (c > p->root_cam ? 1 : 0)); if (stamp[bk] != f) { stamp[bk] = f; ncs++; } }
                 if (slots_m && m != p->root_marker) { const size_t bk = (size_t)(p->nrc + m - (m > p->root_marker ? 1 : 0)); if (stamp[bk] != f) { stamp[bk] = f; nms++; } }
+                if (slots_i) { const size_t bk = (size_t)(p->nrc + p->nrm + 2 * c); if (stamp[bk] != f) { stamp[bk] = f; nis++; } }
             }
-            cs_cum[(size_t)f + 1] = ncs; ms_cum[(size_t)f + 1] = nms;
+            cs_cum[(size_t)f + 1] = ncs; ms_cum[(size_t)f + 1] = nms; is_cnt[(size_t)f + 1] = nis;
         }
     });
     p->max_slots = 0; p->max_ms = 0; p->schur_fma = 0;
     for (int f = 0; f < Fl; f++) {
-        const int ncs = cs_cum[(size_t)f + 1], nms = ms_cum[(size_t)f + 1];
-        slot_ptr[(size_t)f + 1] = slot_ptr[(size_t)f] + ncs + nms;
+        const int ncs = cs_cum[(size_t)f + 1], nms = ms_cum[(size_t)f + 1], nis = is_cnt[(size_t)f + 1];
+        slot_ptr[(size_t)f + 1] = slot_ptr[(size_t)f] + ncs + nms + nis;
         cs_cum[(size_t)f + 1] += cs_cum[(size_t)f]; ms_cum[(size_t)f + 1] += ms_cum[(size_t)f];
-        p->max_slots = std::max(p->max_slots, ncs + nms); p->max_ms = std::max(p->max_ms, nms);
-        const long long nf = 6LL * (ncs + nms); p->schur_fma += 6 * nf * (nf + 1) / 2;
+        p->max_slots = std::max(p->max_slots, ncs + nms + nis); p->max_ms = std::max(p->max_ms, nms);
+        const long long nf = 6LL * (ncs + nms + nis); p->schur_fma += 6 * nf * (nf + 1) / 2;
     }
     p->nslots = (long long)slot_ptr[(size_t)Fl];
     std::vector<int> slot_block((size_t)p->nslots), slot_frame((size_t)p->nslots), frame_block_slot((size_t)std::max(Fl, 1) * std::max(nblk_r, 1));
@@ -543,6 +560,12 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
                     const int bk = p->nrc + m - (m > p->root_marker ? 1 : 0);
                     if (seen[(size_t)bk] < first) { seen[(size_t)bk] = next; slot_block[(size_t)next++] = bk; }
                     slot_m[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
+                }
+            if (slots_i)
+                for (long long o = o0; o < o1; o++) {
+                    const int bk = p->nrc + p->nrm + 2 * p->g_cam[(size_t)o];
+                    if (seen[(size_t)bk] < first) { seen[(size_t)bk] = next; slot_block[(size_t)next++] = bk; }
+                    slot_i[(size_t)(o - p->o_begin)] = seen[(size_t)bk];
                 }
             for (int sl = first; sl < next; sl++) { slot_frame[(size_t)sl] = (int)f; frame_block_slot[(size_t)f * nblk_r + slot_block[(size_t)sl]] = sl; }
         }
@@ -607,7 +630,9 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         {   // descriptors of k_asm_pairs: (first row, rows, frame, W slot) and the camera of every pair
             std::vector<int> pair_cam((size_t)p->npairs);
             for (int pr = 0; pr < p->npairs; pr++) { int4 &pi = pair_info[(size_t)pr]; pair_cam[(size_t)pr] = pi.w; pi.w = slot_c[(size_t)pi.x]; }
-            UP(p->d_pair_info, pair_info); UP(p->d_pair_cam, pair_cam);
+            std::vector<int> pair_slot_i((size_t)p->npairs, -1);
+            for (int pr = 0; pr < p->npairs; pr++) pair_slot_i[(size_t)pr] = slot_i[(size_t)pair_info[(size_t)pr].x];
+            UP(p->d_pair_info, pair_info); UP(p->d_pair_cam, pair_cam); UP(p->d_pair_slot_i, pair_slot_i);
         }
         std::vector<int> perm_fm; std::vector<int4> mrun_info;
         if (p->opt_m) {
@@ -641,7 +666,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);
     CU(p->d_pair_tab.alloc((size_t)std::max(p->npairs, 1) * PAIR_TAB));
-    UP(p->d_intr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
+    UP(p->d_intr, intr); UP(p->d_intr_tr, intr); UP(p->d_K9, p->cam_K); UP(p->d_dist5, p->cam_dist);
     UP(p->d_cam_fixed, fixed_c); UP(p->d_mk_fixed, fixed_m); UP(p->d_fr_fixed, fixed_f);
 #undef UP
     CU(p->d_und_a.alloc((size_t)Nl)); CU(p->d_und_b.alloc((size_t)Nl));
@@ -662,12 +687,13 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     dp.C = p->C; dp.M = p->M; dp.F = Fl; dp.N = Nl; dp.root_cam = p->root_cam; dp.root_marker = p->root_marker;
     dp.opt_c = p->opt_c; dp.opt_m = p->opt_m; dp.opt_f = p->opt_f; dp.huber = p->huber;
     dp.nrc = p->nrc; dp.nrm = p->nrm; dp.n_r = p->n_r; dp.col_frame0 = p->n_r + 6 * p->f_begin;
+    dp.opt_i = p->opt_i; dp.nri = p->nri; dp.col_intr0 = 6 * (p->nrc + p->nrm);
     dp.h = (double)(p->marker_size / 2.f); // aruco::Marker::get3DPoints: half size in float (marker.cpp:358-369)
     dp.J_delta = p->J_delta;
     dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
     dp.obs_pair = p->d_obs_pair.p; dp.pair_fc = p->d_pair_fc.p; dp.npairs = p->npairs; dp.pair_tab = p->d_pair_tab.p;
     dp.und_a = p->d_und_a.p; dp.und_b = p->d_und_b.p; dp.raw_a = p->d_raw_a.p; dp.raw_b = p->d_raw_b.p;
-    dp.intr = p->d_intr.p; dp.frame_slot_ptr = p->d_frame_slot_ptr.p; dp.slot_block = p->d_slot_block.p;
+    dp.intr = p->d_intr.p; dp.intr_tr = p->opt_i ? p->d_intr_tr.p : p->d_intr.p; dp.frame_slot_ptr = p->d_frame_slot_ptr.p; dp.slot_block = p->d_slot_block.p;
     dp.frame_cs_cum = p->d_frame_cs_cum.p;
     dp.cam_tab = p->d_cam_tab.p; dp.mk_tab = p->d_mk_tab.p; dp.fr_tab = p->d_fr_tab.p; dp.cam_tr = p->d_cam_tr.p; dp.mk_tr = p->d_mk_tr.p; dp.fr_tr = p->d_fr_tr.p;
     dp.cam_fixed = p->d_cam_fixed.p; dp.mk_fixed = p->d_mk_fixed.p; dp.fr_fixed = p->d_fr_fixed.p;
@@ -737,7 +763,7 @@ void aar_problem_destroy(aar_problem *p) {
     delete p;
 }
 
-int64_t aar_num_vars(const aar_problem *p) { return p ? p->n_vars : 0; }
+int64_t aar_num_vars(const aar_problem *p) { return p ? p->n_vars_ext : 0; }
 int64_t aar_num_observations(const aar_problem *p) { return p ? p->N : 0; }
 int64_t aar_num_local_observations(const aar_problem *p) { return p ? p->o_end - p->o_begin : 0; }
 int64_t aar_jacobian_nnz(const aar_problem *p) {
@@ -745,7 +771,7 @@ int64_t aar_jacobian_nnz(const aar_problem *p) {
     long long nnz = 0;
     for (long long o = 0; o < p->N; o++) {
         if (!p->g_hasjac[(size_t)o]) continue;
-        nnz += 48LL * ((col_cam(p, p->g_cam[(size_t)o]) >= 0) + (col_marker(p, p->g_marker[(size_t)o]) >= 0) + (p->opt_f ? 1 : 0));
+        nnz += 48LL * ((col_cam(p, p->g_cam[(size_t)o]) >= 0) + (col_marker(p, p->g_marker[(size_t)o]) >= 0) + (p->opt_f ? 1 : 0)) + (p->opt_i ? 72 : 0);
     }
     return nnz;
 }
@@ -795,11 +821,51 @@ int aar_mats2evec(const aar_problem *p, double *z) {
     if (p->opt_c) for (int i = 0; i < p->C; i++) if (i != p->root_cam) put(&p->cam_T[16 * (size_t)i]);
     if (p->opt_m) for (int i = 0; i < p->M; i++) if (i != p->root_marker) put(&p->marker_T[16 * (size_t)i]);
     if (p->opt_f) for (int i = 0; i < p->F; i++) put(&p->frame_T[16 * (size_t)i]);
+    if (p->opt_i)                                            // fill_io_vec_cam_intrinsics (multicam_mapper.cpp:488-498)
+        for (int c = 0; c < p->C; c++) {
+            const double *K = &p->cam_K[9 * (size_t)c];
+            z[vi] = K[0]; z[vi + 1] = K[2]; z[vi + 2] = K[4]; z[vi + 3] = K[5];
+            for (int k = 0; k < 5; k++) z[vi + 4 + k] = p->cam_dist[5 * (size_t)c + k];
+            vi += 9;
+        }
     return AAR_OK;
 }
 
+// io_vec of the reference [cameras | markers | frames | 9 per camera: fx cx fy cy k1 k2 p1 p2 k3] (multicam_mapper.cpp:445-461,
+// 488-522) <-> internal z [cameras | markers | 12 per camera: fx cx fy cy k1 k2 | p1 p2 k3 . . . | frames] (aar_intrinsics.cuh).
+// Identity unless the intrinsics are optimised.
+static void z_ext2int(const aar_problem *p, const double *ze, double *zi) {
+    const size_t np = 6 * (size_t)(p->nrc + p->nrm), nf = p->opt_f ? 6 * (size_t)p->F : 0;
+    std::memcpy(zi, ze, np * sizeof(double));
+    for (int c = 0; c < p->C; c++) { double *d = zi + np + 12 * (size_t)c; std::memcpy(d, ze + np + nf + 9 * (size_t)c, 9 * sizeof(double)); d[9] = d[10] = d[11] = 0.0; }
+    std::memcpy(zi + (size_t)p->n_r, ze + np, nf * sizeof(double));
+}
+static void z_int2ext(const aar_problem *p, const double *zi, double *ze) {
+    const size_t np = 6 * (size_t)(p->nrc + p->nrm), nf = p->opt_f ? 6 * (size_t)p->F : 0;
+    std::memcpy(ze, zi, np * sizeof(double));
+    std::memcpy(ze + np, zi + (size_t)p->n_r, nf * sizeof(double));
+    for (int c = 0; c < p->C; c++) std::memcpy(ze + np + nf + 9 * (size_t)c, zi + np + 12 * (size_t)c, 9 * sizeof(double));
+}
 static int upload_z(aar_problem *p, const double *z, double *dst) {
-    if (p->n_vars > 0) CU(cudaMemcpyAsync(dst, z, (size_t)p->n_vars * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (p->n_vars <= 0) return AAR_OK;
+    if (p->opt_i) {
+        CU(cudaStreamSynchronize(p->stream));               // the staging vector may still feed an earlier copy
+        p->z_stage.resize((size_t)p->n_vars);
+        z_ext2int(p, z, p->z_stage.data());
+        z = p->z_stage.data();
+    }
+    CU(cudaMemcpyAsync(dst, z, (size_t)p->n_vars * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    return AAR_OK;
+}
+// device z (internal order) -> caller's io_vec; the stream is synchronised on return when the intrinsics are optimised
+static int download_z(aar_problem *p, const double *src, double *z_out) {
+    if (p->n_vars <= 0) return AAR_OK;
+    if (!p->opt_i) { CU(cudaMemcpyAsync(z_out, src, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToHost, p->stream)); return AAR_OK; }
+    CU(cudaStreamSynchronize(p->stream));
+    p->z_stage.resize((size_t)p->n_vars);
+    CU(cudaMemcpyAsync(p->z_stage.data(), src, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    z_int2ext(p, p->z_stage.data(), z_out);
     return AAR_OK;
 }
 
@@ -854,8 +920,9 @@ int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t 
     const size_t nj = 144 * (size_t)std::max<long long>(p->N, 1);
     if (p->d_J.n < nj) CU(p->d_J.alloc(nj));
     if ((rc = jacobian_accumulate(p, p->huber_eval, p->d_J.p))) return rc;
-    std::vector<double> J(nj);
+    std::vector<double> J(nj), Ji(p->opt_i ? 32 * (size_t)std::max<long long>(p->N, 1) : 0);
     CU(cudaMemcpyAsync(J.data(), p->d_J.p, nj * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (p->opt_i && p->N > 0) CU(cudaMemcpyAsync(Ji.data(), p->d_Ji.p, 32 * (size_t)p->N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     CU(cudaGetLastError());
     // compressed columns in the order setFromTriplets leaves them: columns ascending, rows ascending
@@ -876,6 +943,13 @@ int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t 
     if (p->opt_c) for (int i = 0; i < p->C; i++) if (i != p->root_cam) emit(by_cam[(size_t)i], 0);
     if (p->opt_m) for (int i = 0; i < p->M; i++) if (i != p->root_marker) emit(by_marker[(size_t)i], 6);
     if (p->opt_f) for (int i = 0; i < p->F; i++) emit(by_frame[(size_t)i], 12);
+    if (p->opt_i)                                            // 9 columns per camera, root included; the distortion columns are explicit zeros (mcm.cpp:835-893)
+        for (int i = 0; i < p->C; i++)
+            for (int d = 0; d < 9; d++) {
+                for (long long o : by_cam[(size_t)i])
+                    for (int q = 0; q < 8; q++) { rowidx[nnz] = (int32_t)(8 * o + q); vals[nnz] = d < 4 ? Ji[(size_t)o * 32 + (size_t)d * 8 + q] : 0.0; nnz++; }
+                colptr[++col] = nnz;
+            }
     return AAR_OK;
 }
 
@@ -1056,8 +1130,8 @@ int aar_lm_end(aar_problem *p, double *z_out) {
             if (fb > (size_t)p->n_r) CU(cudaMemsetAsync(p->d_zt.p + p->n_r, 0, (fb - (size_t)p->n_r) * sizeof(double), p->stream));
             if (fe < n) CU(cudaMemsetAsync(p->d_zt.p + fe, 0, (n - fe) * sizeof(double), p->stream));
             int rc = allreduce(p, p->d_zt.p, n, ncclSum); if (rc) return rc;
-            CU(cudaMemcpyAsync(z_out, p->d_zt.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-        } else CU(cudaMemcpyAsync(z_out, p->d_z.p, (size_t)p->n_vars * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            if ((rc = download_z(p, p->d_zt.p, z_out))) return rc;
+        } else { int rc = download_z(p, p->d_z.p, z_out); if (rc) return rc; }
     }
     CU(cudaStreamSynchronize(p->stream));
     p->lm_active = false;

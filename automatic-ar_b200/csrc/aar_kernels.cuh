@@ -31,7 +31,9 @@ struct DevProblem {
     int npairs;
     double *pair_tab;            // [npairs][PAIR_TAB]: inv(Tc) * To and its perturbed variants (aar_jacobian.cuh: k_pair_tab)
     const float4 *und_a, *und_b, *raw_a, *raw_b; // x0 y0 x1 y1 | x2 y2 x3 y3
-    const double *intr;          // [C][4] fx cx fy cy
+    double *intr;                // [C][4] fx cx fy cy at z (constant unless the intrinsics are optimised: then written by k_expand_intr)
+    double *intr_tr;             // the same at the trial point (k_residual); == intr when the intrinsics are fixed
+    int opt_i, nri, col_intr0;   // intrinsics optimised; 2 C pseudo-blocks behind the pose blocks; their first column in the internal z (aar_intrinsics.cuh)
     // frame CSR of W slots: per frame the camera blocks seen (in order of first appearance), then the marker blocks
     const int *frame_slot_ptr;   // [F+1]
     const int *frame_cs_cum;     // [F+1] camera slots before frame f (so the marker slots of f start at slot_ptr[f] + cs_cum[f+1] - cs_cum[f])
@@ -129,6 +131,7 @@ __device__ __forceinline__ void load8(const float4 *a, const float4 *b, long lon
 
 #include "aar_jacobian.cuh"
 #include "aar_assemble.cuh"
+#include "aar_intrinsics.cuh"
 
 namespace aar {
 
@@ -140,7 +143,7 @@ __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam
     double acc = 0;
     if (o < p.N) {
         int cm = p.obs_cm[o], f = p.obs_f[o], c = obs_cam(cm), m = obs_marker(cm);
-        Intr k; k.fx = p.intr[4 * c]; k.cx = p.intr[4 * c + 1]; k.fy = p.intr[4 * c + 2]; k.cy = p.intr[4 * c + 3];
+        Intr k; k.fx = p.intr_tr[4 * c]; k.cx = p.intr_tr[4 * c + 1]; k.fy = p.intr_tr[4 * c + 2]; k.cy = p.intr_tr[4 * c + 3];
         Pose ci, To, Tm, T1;
         load_pose(To, fr + (size_t)f * fr_stride);
         bool cam_root = c == p.root_cam, mk_root = m == p.root_marker;

@@ -130,24 +130,16 @@ void MultiCamMapper::init(size_t root_c, const std::map<int, Mat44> &Tc, size_t 
         cam_configs[p.first] = cc[(size_t)p.first];
     }
     corners_undistorted = false;
-    // the handle of init() only runs remove_distortions; the reference's default Config has optimize_cam_intrinsics = true
-    // (find_solution switches it off before solve()), which the device path refuses — solve() reports that, not init()
-    Config keep = config; config.optimize_cam_intrinsics = false;
     make_handle(false);
     pull_undistorted();                                          // remove_distortions (:554-578) ran on the device
-    config = keep;
-    if (config.optimize_cam_intrinsics) drop_handle();
 }
 
 void MultiCamMapper::init(const std::map<int, Mat44> &object_poses, const FrameCamMarkers &fcm) {
     drop_handle();
     object_to_global = object_poses; frame_cam_markers = fcm; raw_frame_cam_markers = fcm;
     corners_undistorted = false;
-    Config keep = config; config.optimize_cam_intrinsics = false;
     make_handle(false);
     pull_undistorted();
-    config = keep;
-    if (config.optimize_cam_intrinsics) drop_handle();
 }
 
 void MultiCamMapper::make_handle(bool undist) {
@@ -175,7 +167,6 @@ void MultiCamMapper::make_handle(bool undist) {
     d.optimize_cam_poses = config.optimize_cam_poses; d.optimize_marker_poses = config.optimize_marker_poses; d.optimize_object_poses = config.optimize_object_poses;
     d.optimize_cam_intrinsics = config.optimize_cam_intrinsics; d.with_huber = with_huber; d.corners_undistorted = undist;
     d.J_delta = 1e-3; d.device = 0; d.world_size = 1;
-    // the device path has no intrinsics block: a Config that asks for it is refused like any other unsupported input
     check(aar_problem_create(&d, &handle), "aar_problem_create");
 }
 
@@ -252,6 +243,15 @@ void MultiCamMapper::solve() {
     if (config.optimize_marker_poses) for (auto &p : transforms_to_root_marker) { std::memcpy(p.second.m, &Tm[16 * i], sizeof p.second.m); i++; }
     i = 0;
     if (config.optimize_object_poses) for (auto &p : object_to_global) { std::memcpy(p.second.m, &To[16 * i], sizeof p.second.m); i++; }
+    if (config.optimize_cam_intrinsics) {                        // intrinsics_vec2mats (:580-593): the last 9 entries per camera
+        size_t vi = io_vec.size() - 9 * C;
+        for (auto &p : transforms_to_root_cam) {
+            CamConfig &cc = cam_configs[p.first];
+            cc.K[0] = io_vec[vi]; cc.K[2] = io_vec[vi + 1]; cc.K[4] = io_vec[vi + 2]; cc.K[5] = io_vec[vi + 3];
+            for (int k = 0; k < 5; k++) cc.dist[k] = io_vec[vi + 4 + k];
+            vi += 9;
+        }
+    }
 }
 
 void MultiCamMapper::track() {

@@ -2,6 +2,7 @@
 //   solution_tool roundtrip <in.solution> <out.solution> [<out.yaml>]     read + write back (must be byte identical)
 //   solution_tool detections <in.detections> <out.detections>             read + write back
 //   solution_tool calib <data_folder> -                                   CamConfig::read_cam_configs: one line per camera, %.17g
+//   solution_tool resolve_full <in.solution> <out.solution>               (GPU) the same with the default Config (camera intrinsics optimised too)
 //   solution_tool resolve <in.solution> <out.solution>                    (GPU) re-create the mapper through the 8-argument
 //                         init() — the Initializer-output path: raw corners, device undistortion — and solve()
 #include <algorithm>
@@ -29,7 +30,7 @@ int main(int argc, char **argv) {
                 for (int i = 0; i < 5; i++) std::printf(" %.17g", c.dist[i]);
                 std::printf("\n");
             }
-        } else if (mode == "resolve") {
+        } else if (mode == "resolve" || mode == "resolve_full") {
             aar::MultiCamMapper in;
             if (!in.read_solution_file(argv[2])) return 1;
             int max_id = -1; for (auto &c : in.cam_configs) max_id = std::max(max_id, c.first);
@@ -37,7 +38,7 @@ int main(int argc, char **argv) {
             for (auto &c : in.cam_configs) confs[(size_t)c.first] = c.second;
             aar::MultiCamMapper mcm(in.get_root_cam(), in.transforms_to_root_cam, in.get_root_marker(), in.transforms_to_root_marker, in.object_to_global,
                                     in.frame_cam_markers, (float)in.get_marker_size(), confs);
-            mcm.set_optmize_flag_cam_intrinsics(false);
+            if (mode == "resolve") mcm.set_optmize_flag_cam_intrinsics(false);      // resolve_full: MultiCamMapper's default Config, intrinsics included
             mcm.solve();
             std::cout.precision(17); std::cout << "final_error: " << mcm.final_error << " iterations: " << mcm.iterations << std::endl;
             if (!mcm.write_solution_file(argv[3])) return 1;

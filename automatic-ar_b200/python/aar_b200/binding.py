@@ -122,7 +122,7 @@ class Problem:
         return dict(frame_idx=of, cam_idx=oc, marker_idx=om, has_jac=oj)
 
     @staticmethod
-    def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta):
+    def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics=False):
         k = {}
         k["cam_ids"] = np.ascontiguousarray(rig.cam_ids, np.int32); k["marker_ids"] = np.ascontiguousarray(rig.marker_ids, np.int32)
         k["frame_ids"] = np.ascontiguousarray(rig.frame_ids, np.int32)
@@ -139,20 +139,21 @@ class Problem:
         d.cam_T, d.marker_T, d.frame_T, d.cam_K, d.cam_dist = _vp(k["cam_T"]), _vp(k["marker_T"]), _vp(k["frame_T"]), _vp(k["K"]), _vp(k["dist"])
         d.num_detections = len(k["det_frame"])
         d.det_frame, d.det_cam, d.det_marker, d.det_xy = _vp(k["det_frame"]), _vp(k["det_cam"]), _vp(k["det_marker"]), _vp(k["det_xy"])
-        d.optimize_cam_poses, d.optimize_marker_poses, d.optimize_object_poses, d.optimize_cam_intrinsics = int(cams), int(markers), int(objects), 0
+        d.optimize_cam_poses, d.optimize_marker_poses, d.optimize_object_poses, d.optimize_cam_intrinsics = int(cams), int(markers), int(objects), int(intrinsics)
         d.with_huber = int(with_huber); d.J_delta = J_delta; d.device = device
         d.stream = C.c_void_p(stream) if stream else None
         d.rank, d.world_size = rank, world_size
         return d, k
 
     def __init__(self, rig, use_init=True, cams=True, markers=True, objects=True, with_huber=False, device=0, stream=None,
-                 rank=0, world_size=1, J_delta=0.0):
+                 rank=0, world_size=1, J_delta=0.0, intrinsics=False):
         L = lib()
-        d, self._keep = self._desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta)
+        d, self._keep = self._desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics)
         self.h = C.c_void_p()
         _chk(L.aar_problem_create(C.byref(d), C.byref(self.h)), "aar_problem_create")
         self.nC, self.nM, self.nF = d.num_cams, d.num_markers, d.num_frames
-        self.n_r = 6 * ((self.nC - 1 if cams else 0) + (self.nM - 1 if markers else 0))
+        # reduced system: pose blocks, then two 6-wide pseudo-blocks per camera when the intrinsics are optimised (csrc/aar_intrinsics.cuh)
+        self.n_r = 6 * ((self.nC - 1 if cams else 0) + (self.nM - 1 if markers else 0) + (2 * self.nC if intrinsics else 0))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:

@@ -387,3 +387,66 @@ def test_tensor_core_assembly_matches_oracle_and_legacy_kernel(binding, oracle_m
                 S_o, b_o, _ = o.reduced_system(z0, 5.0)
                 if len(b0):
                     assert np.abs(S1[iu] - S_o[iu]).max() <= 1e-10 * np.abs(S_o).max() and np.abs(b1 - b_o).max() <= 1e-10 * np.abs(b_o).max(), (huber, cams, markers, objects)
+
+
+# ------------------------------------------------------------------ camera-intrinsics block
+def _with_intrinsics(rig):
+    """Columns of io_vec with optimize_cam_intrinsics on: [cams | markers | frames | 9 per camera] (multicam_mapper.cpp:445-461)."""
+    z_intr = np.concatenate([np.concatenate([[rig.K[c, 0, 0], rig.K[c, 0, 2], rig.K[c, 1, 1], rig.K[c, 1, 2]], rig.dist[c]]) for c in range(rig.C)])
+    return z_intr
+
+
+@pytest.mark.parametrize("distorted", [False, True])
+def test_intrinsics_block_jacobian_and_residual_bit_exact(binding, oracle_mod, distorted):
+    """MultiCamMapper's default Config optimises the camera intrinsics too (multicam_mapper.h:75-81; find_solution switches it off):
+    9 columns per camera — fx, cx, fy, cy by central differences, the five distortion columns structurally present and zero
+    (multicam_mapper.cpp:835-893) — and projections that read K from io_vec."""
+    rig = small_rig(seed=13, C=3, M=5, F=30, distorted=distorted)
+    o = oracle_mod.Oracle(rig); o.set_config(intrinsics=True)
+    p = binding.Problem(rig, intrinsics=True)
+    z = o.mats2evec()
+    assert p.num_vars == o.num_vars == 6 * (rig.C - 1 + rig.M - 1 + rig.F) + 9 * rig.C
+    assert np.array_equal(p.mats2evec()[-9 * rig.C:], _with_intrinsics(rig)) and np.array_equal(z[-9 * rig.C:], _with_intrinsics(rig))
+    rng = np.random.default_rng(2)
+    for trial in range(2):
+        zz = z.copy()
+        if trial:      # move every parameter, the intrinsics included: the projections must follow io_vec, not the camera files
+            zz += rng.normal(0, 1e-3, len(zz)); zz[-9 * rig.C:] += rng.normal(0, 0.5, 9 * rig.C)
+        r_g, _ = p.residual(zz)
+        assert np.array_equal(r_g, o.error(zz))
+        cp_o, ri_o, v_o = o.jacobian(zz)
+        cp_g, ri_g, v_g = p.jacobian(zz)
+        assert p.jacobian_nnz == len(v_o)
+        assert np.array_equal(cp_o, cp_g) and np.array_equal(ri_o, ri_g)
+        assert np.array_equal(v_o, v_g), np.abs(v_o - v_g).max()
+    n0 = 6 * (rig.C - 1 + rig.M - 1 + rig.F)
+    nz_cols = [np.any(v_g[cp_g[n0 + 9 * c + k]:cp_g[n0 + 9 * c + k + 1]] != 0) for c in range(rig.C) for k in range(9)]
+    assert nz_cols == [True] * 4 + [False] * 5 + [True] * 4 + [False] * 5 + [True] * 4 + [False] * 5
+    parity_record("intrinsics_block_jacobian_vs_oracle", distorted=bool(distorted), nnz=int(len(v_g)), bit_exact=True)
+
+
+def test_intrinsics_block_lm_steps_and_solve(binding, oracle_mod):
+    """SparseLevMarq::step with the intrinsics columns in the system: per-iteration cost / z against the reference solver driving the
+    restated MultiCamMapper; end point against its reproducibility envelope."""
+    rig = small_rig(seed=14, C=3, M=6, F=40)
+    o = oracle_mod.Oracle(rig); o.set_config(intrinsics=True)
+    p = binding.Problem(rig, intrinsics=True)
+    z0 = o.mats2evec()
+    worst = 0.0
+    for steps in (1, 2, 3):
+        o.set_max_iters(steps)
+        z_o, c_o, it_o, tr_o = o.solve(z0)
+        prm = binding.Problem.default_params(max_iters=steps, ignore_stop_rules=1)
+        z_g, c_g, it_g, tr_g = p.solve(z0, prm)
+        dz = np.abs(z_g - z_o).max() / max(np.abs(z_o).max(), 1.0); dc = abs(c_g - c_o) / c_o
+        worst = max(worst, dz, dc)
+        assert dz <= 1e-10 and dc <= 1e-10, (steps, dz, dc)
+        assert np.array_equal(z_g[-9 * rig.C:].reshape(-1, 9)[:, 4:], z0[-9 * rig.C:].reshape(-1, 9)[:, 4:])     # zero columns: the distortion coefficients never move
+    o.set_max_iters(10000)
+    z_o, c_o, it_o, tr_o = o.solve(z0)
+    z_g, c_g, it_g, tr_g = p.solve(z0)
+    env_c, env_z = _oracle_envelope(o, z0, c_o, z_o)
+    d_cost = abs(c_g - c_o) / c_o
+    parity_record("intrinsics_block_lm_vs_reference_solver", first_steps_worst_rel_dev=worst, iterations=[int(it_g), int(it_o)], final_cost=[float(c_g), float(c_o)],
+                  rel_dev_final_cost=d_cost, ref_envelope_cost=env_c, north_star=1e-6)
+    _end_point_bar(d_cost, env_c, 2e-5)

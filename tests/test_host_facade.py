@@ -196,3 +196,22 @@ def test_track_app(host_bins, tmp_path):
     off = 6 * (rig.C - 1) + 6 * (rig.M - 1)
     t_est = res["vec"][off:off + 6 * rig.F].reshape(-1, 6)[:, 3:]
     assert np.abs(t_est - rig.T_frame_true[:, :3, 3]).max() < 5e-3    # object positions recovered to a few mm
+
+
+@pytest.mark.gpu
+def test_default_config_with_intrinsics_through_the_facade(host_bins, tmp_path):
+    """MultiCamMapper's default Config (multicam_mapper.h:75-81) optimises the camera intrinsics as well: the facade must hand the
+    9 values per camera to the device path and read them back into the camera configurations written to the .solution file."""
+    from aar_b200 import binding
+    rig = synth.make_config("cfg1")
+    a, b = str(tmp_path / "initial.solution"), str(tmp_path / "full.solution")
+    synth.write_solution_file(a, rig)
+    out = subprocess.run([os.path.join(host_bins, "solution_tool"), "resolve_full", a, b], check=True, capture_output=True, text=True).stdout
+    cost = float(out.split("final_error:")[1].split()[0])
+    p = binding.Problem(rig, intrinsics=True)
+    z, fc, it, tr = p.solve(p.mats2evec())
+    assert abs(cost - fc) <= 2e-5 * fc
+    res = synth.read_solution_file(b)
+    got = res["vec"][-9 * rig.C:].reshape(-1, 9); want = z[-9 * rig.C:].reshape(-1, 9)
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max() and np.abs(got[:, :4] - rig.K[:, [0, 0, 1, 1], [0, 2, 1, 2]]).max() > 1e-6   # they moved
+    assert res["flags"] == (True, True, True, True)
