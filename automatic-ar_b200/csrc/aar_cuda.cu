@@ -125,6 +125,10 @@ struct aar_problem {
     ncclComm_t comm = nullptr;
     // ---- instrumentation
     long long launches = 0; bool profiling = false;
+    // graph-resident LM loop (aar_lm_iterate): two nested WHILE nodes, conditions set by k_lm_decide_g / k_lm_iter_end_g
+    cudaGraph_t lm_graph = nullptr; cudaGraphExec_t lm_exec = nullptr; cudaGraphConditionalHandle lm_outer = 0, lm_inner = 0; cudaStream_t lm_side = nullptr;
+    bool lm_graph_tried = false, lm_graph_ok = false, capturing = false; long long lm_graph_launches = 0, lm_graph_iters = 0; int lm_body_launches = 0, lm_try_launches = 0;
+    DevBuf<LmTraceDev> d_trace;
     cudaEvent_t ev[16] = {}; double phase_ms[AAR_NUM_PHASES] = {};
 };
 
@@ -308,7 +312,7 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
         if (exact) { if (p->d_Jn64.n < JROW * Np) CU(p->d_Jn64.alloc(JROW * Np)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
         else { if (p->d_Jn32.n < JROW * Np) CU(p->d_Jn32.alloc(JROW * Np)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
         if (rc) return rc;
-        if (exact) break;
+        if (exact || p->capturing) break;      // graph-resident loop: k_lm_begin_iter_g looks at the flag on the device and hands the iteration back
         // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
         CU(cudaMemcpyAsync(p->h_flags, p->d_flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
@@ -687,7 +691,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     dp.C = p->C; dp.M = p->M; dp.F = Fl; dp.N = Nl; dp.root_cam = p->root_cam; dp.root_marker = p->root_marker;
     dp.opt_c = p->opt_c; dp.opt_m = p->opt_m; dp.opt_f = p->opt_f; dp.huber = p->huber;
     dp.nrc = p->nrc; dp.nrm = p->nrm; dp.n_r = p->n_r; dp.col_frame0 = p->n_r + 6 * p->f_begin;
-    dp.opt_i = p->opt_i; dp.nri = p->nri; dp.col_intr0 = 6 * (p->nrc + p->nrm);
+    dp.opt_i = p->opt_i; dp.nri = p->nri; dp.col_intr0 = 6 * (p->nrc + p->nrm); dp.st_dev = nullptr;
     dp.h = (double)(p->marker_size / 2.f); // aruco::Marker::get3DPoints: half size in float (marker.cpp:358-369)
     dp.J_delta = p->J_delta;
     dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
@@ -759,6 +763,9 @@ void aar_problem_destroy(aar_problem *p) {
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_red3) cudaFreeHost(p->h_red3);
     if (p->h_flags) cudaFreeHost(p->h_flags);
+    if (p->lm_exec) cudaGraphExecDestroy(p->lm_exec);
+    if (p->lm_graph) cudaGraphDestroy(p->lm_graph);
+    if (p->lm_side) cudaStreamDestroy(p->lm_side);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -1008,6 +1015,114 @@ int aar_lm_begin(aar_problem *p, const double *z0, const aar_lm_params *params) 
     return AAR_OK;
 }
 
+
+// ------------------------------------------------------------------------------- graph-resident LM loop ----
+// SparseLevMarq::solve (sparselevmarq.h:439-472) with the do-while of step() (:384-419) as two nested CUDA-graph WHILE nodes:
+//   WHILE outer { J^T J assembly; k_lm_begin_iter_g; WHILE inner { Schur + reduced solve + back substitution + trial residual;
+//                 k_lm_decide_g; k_lm_commit }; k_lm_iter_end_g }
+// Nothing returns to the host between the launch of the graph and its end: the accept / reject decision, the damping update,
+// the stop rules, the hubberDelta annealing and the per-iteration trace all live in LmState on the device.  The first LM iteration
+// of a solve always runs on the host-driven path (it sizes the scratch buffers and computes mu0, which needs a MAX all-reduce
+// when sharded); sharded handles (NCCL inside a conditional body), profiling and verbose mode stay on the host-driven path.
+constexpr int LM_TRACE_DEV_CAP = 4096;
+#define GR(call)                                                                                          \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); ok = false; goto done; } } while (0)
+
+static bool lm_graph_build(aar_problem *p) {
+    p->lm_graph_tried = true;
+    bool ok = true;
+    cudaStream_t main_stream = p->stream;
+    const long long launches_before = p->launches;
+    const int n_r = p->n_r;
+    double *S = p->d_red.p, *Br = S + (size_t)n_r * n_r + n_r;
+    cudaGraph_t body_outer = nullptr, body_inner = nullptr, tmp = nullptr;
+    cudaGraphNode_t node_outer, node_inner;
+    bool cap_outer = false, cap_inner = false;
+    cudaGraphNodeParams np = {}, ni = {};
+    cudaStreamCaptureStatus cs; const cudaGraphNode_t *deps = nullptr; size_t ndeps = 0; cudaGraph_t cg = nullptr;
+    long long l0 = 0;
+    if (cudaStreamCreateWithFlags(&p->lm_side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (p->d_trace.alloc(LM_TRACE_DEV_CAP) != cudaSuccess) { cudaGetLastError(); return false; }
+    GR(cudaGraphCreate(&p->lm_graph, 0));
+    GR(cudaGraphConditionalHandleCreate(&p->lm_outer, p->lm_graph, 1, cudaGraphCondAssignDefault));
+    GR(cudaGraphConditionalHandleCreate(&p->lm_inner, p->lm_graph, 0, 0));
+    std::memset(&np, 0, sizeof np);
+    np.type = cudaGraphNodeTypeConditional; np.conditional.handle = p->lm_outer; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+    GR(cudaGraphAddNode(&node_outer, p->lm_graph, nullptr, 0, &np));
+    body_outer = np.conditional.phGraph_out[0];
+    p->capturing = true; p->dp.st_dev = p->d_st.p;
+    GR(cudaStreamBeginCaptureToGraph(main_stream, body_outer, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)); cap_outer = true;
+    if (jacobian_accumulate(p, 0.f, nullptr)) { ok = false; goto done; }
+    k_lm_begin_iter_g<<<1, 1, 0, main_stream>>>(p->d_st.p, p->d_flag.p, p->lm_inner); p->launches++;
+    // the inner WHILE node goes in by hand, behind everything captured so far; the capture continues behind it
+    GR(cudaStreamGetCaptureInfo_v2(main_stream, &cs, nullptr, &cg, &deps, &ndeps));
+    std::memset(&ni, 0, sizeof ni);
+    ni.type = cudaGraphNodeTypeConditional; ni.conditional.handle = p->lm_inner; ni.conditional.type = cudaGraphCondTypeWhile; ni.conditional.size = 1;
+    GR(cudaGraphAddNode(&node_inner, body_outer, deps, ndeps, &ni));
+    body_inner = ni.conditional.phGraph_out[0];
+    GR(cudaStreamUpdateCaptureDependencies(main_stream, &node_inner, 1, cudaStreamSetCaptureDependencies));
+    p->lm_body_launches = (int)(p->launches - launches_before);
+    // one try of the do-while, captured on a side stream into the inner body
+    l0 = p->launches;
+    p->stream = p->lm_side;
+    GR(cudaStreamBeginCaptureToGraph(p->lm_side, body_inner, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)); cap_inner = true;
+    GR(cudaMemsetAsync(p->d_red3.p, 0, 8 * sizeof(double), p->stream));
+    if (build_and_solve_reduced(p)) { ok = false; goto done; }
+    if (p->opt_f && p->dp.F > 0) {
+        k_backsub<<<std::max(1, std::min(4 * p->num_sms, (int)cdiv(p->dp.F, BS_WARPS))), BS_WARPS * 32, 0, p->stream>>>(p->dp, p->d_fc.p, p->d_Hf.p, p->d_W.p, p->d_dr.p, p->d_z.p, p->d_zt.p, p->d_red3.p);
+        p->launches++;
+    }
+    residual(p, p->d_zt.p, 0.f, nullptr);
+    k_lm_decide_g<<<1, 1, 0, p->stream>>>(p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->lm_inner); p->launches++;
+    k_lm_commit<<<std::max(1, std::min(2 * p->num_sms, (int)cdiv(p->n_vars, 256))), 256, 0, p->stream>>>(p->d_st.p, p->n_vars, p->d_zt.p, p->d_z.p); p->launches++;
+    GR(cudaStreamEndCapture(p->lm_side, &tmp)); cap_inner = false;
+    p->stream = main_stream;
+    p->lm_try_launches = (int)(p->launches - l0);
+    k_lm_iter_end_g<<<1, 1, 0, main_stream>>>(p->d_st.p, p->d_flag.p, p->d_trace.p, p->lm_outer); p->launches++;
+    p->lm_body_launches += 1;
+    GR(cudaStreamEndCapture(main_stream, &tmp)); cap_outer = false;
+    GR(cudaGraphInstantiate(&p->lm_exec, p->lm_graph, 0));
+done:
+    p->stream = main_stream;
+    if (cap_inner) { cudaStreamEndCapture(p->lm_side, &tmp); }
+    if (cap_outer) { cudaStreamEndCapture(main_stream, &tmp); }
+    p->capturing = false; p->dp.st_dev = nullptr;
+    p->launches = launches_before;                       // capture is not execution
+    if (!ok) { cudaGetLastError(); if (p->lm_exec) { cudaGraphExecDestroy(p->lm_exec); p->lm_exec = nullptr; } }
+    p->lm_graph_ok = ok;
+    return ok;
+}
+#undef GR
+
+// runs up to `iters` LM iterations inside the graph; one host synchronisation at the end
+static int lm_graph_run(aar_problem *p, int iters, aar_lm_report *rep, int *iters_done, int *must_exit) {
+    const aar_lm_params &P = p->params;
+    LmState &h = *p->h_st;
+    h.huber_delta = p->huber_cur; h.huber_eval = p->huber_eval;
+    h.iters_done = 0; h.max_iters = iters; h.must_exit = 0; h.ignore_stop = P.ignore_stop_rules;
+    h.min_error = P.min_error; h.min_step = P.min_step_error_diff; h.min_avg = P.min_average_step_error_diff; h.rows = (double)(8 * p->N);
+    h.total_tries = 0; h.trace_cap = LM_TRACE_DEV_CAP; h.trace_len = 0;
+    h.cost = p->cost; h.prev_cost = p->prev_cost;
+    int rc;
+    if ((rc = push_state(p))) return rc;
+    CU(cudaGraphLaunch(p->lm_exec, p->stream));
+    if ((rc = fetch_state(p))) return rc;                    // the one synchronisation of the call
+    CU(cudaGetLastError());
+    p->lm_graph_launches++; p->lm_graph_iters += h.iters_done;
+    p->launches += (long long)h.iters_done * p->lm_body_launches + h.total_tries * p->lm_try_launches + (h.must_exit == -2 ? p->lm_body_launches : 0);
+    p->total_tries += h.total_tries; p->iter += h.iters_done;
+    p->cost = h.cost; p->prev_cost = h.prev_cost; p->huber_cur = h.huber_delta; p->huber_eval = h.huber_eval;
+    if (rep && rep->trace && h.trace_len > 0 && rep->trace_len < rep->trace_capacity) {
+        const int n = std::min(h.trace_len, rep->trace_capacity - rep->trace_len);
+        static_assert(sizeof(LmTraceDev) == sizeof(aar_lm_trace), "trace layouts differ");
+        CU(cudaMemcpyAsync(rep->trace + rep->trace_len, p->d_trace.p, (size_t)n * sizeof(aar_lm_trace), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        rep->trace_len += n;
+    }
+    *iters_done = h.iters_done; *must_exit = h.must_exit;
+    return AAR_OK;
+}
+
 int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
     if (!p || !p->lm_active) { set_err("aar_lm_iterate without aar_lm_begin"); return AAR_ERR_INVALID; }
     CU(cudaSetDevice(p->device));
@@ -1018,7 +1133,34 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
     int done_iters = 0; int mustExit = 0;
     if (rep) { rep->trace_len = 0; rep->initial_cost = p->initial_cost; }
     double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
+    const char *no_graph = getenv("AAR_NO_GRAPH");           // development aid: host-driven loop only
+    const bool graph_eligible = !p->comm && !p->profiling && !P.verbose && !p->legacy_acc && !p->force_exact_staging && !(no_graph && *no_graph == '1') && p->dp.N > 0;
     for (int it = 0; it < max_iters && !mustExit; it++) {
+        if (graph_eligible && p->h_st->mu >= 0 && (p->lm_graph_ok || !p->lm_graph_tried)) {
+            // every iteration but the first of a solve: inside the graph, without the host (see lm_graph_build)
+            if (!p->lm_graph_tried) lm_graph_build(p);
+            if (p->lm_graph_ok) {
+                int gd = 0, gx = 0;
+                const int want = std::min(max_iters - it, LM_TRACE_DEV_CAP);
+                if ((rc = lm_graph_run(p, want, rep, &gd, &gx))) { p->lm_active = false; return rc; }
+                done_iters += gd;
+                if (gx == -1) {
+                    int flags[4];
+                    CU(cudaMemcpy(flags, p->d_flag.p, sizeof flags, cudaMemcpyDeviceToHost));
+                    set_err(flags[0] ? "non-positive Cholesky pivot at iteration %d (damped normal equations not positive definite)"
+                                     : flags[2] ? "camera inverse of a translation-perturbed pose changed its rotation at iteration %d (bit-exact table assumption violated)"
+                                                : "non-finite cost at iteration %d", p->iter);
+                    CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
+                    p->lm_active = false;
+                    return AAR_ERR_NUMERIC;
+                }
+                if (gx > 0) { mustExit = gx; break; }
+                it += gd;
+                if (it >= max_iters) break;
+                if (gx == 0) { it--; continue; }              // the graph ran its share of the trace buffer: go again
+                // gx == -2: the float32 staging was inexact in this iteration; it is redone below on the host path (FP64 staging)
+            }
+        }
         // ---- J, JtJ blocks, B (sparselevmarq.h:353-367)
         prof_mark(p, 0);
         if ((rc = zero_normal_equations(p))) return rc;
@@ -1054,13 +1196,15 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             prof_mark(p, 5);
             if ((rc = allreduce(p, p->d_red3.p, 3, ncclSum))) return rc;
             LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br);
+            // an accepted trial point becomes the iterate by a device copy (a pointer swap would invalidate the captured graph of the resident loop)
+            LAUNCH(p, k_lm_commit, std::max(1, std::min(2 * p->num_sms, (int)cdiv(p->n_vars, 256))), 256, 0, p->d_st.p, p->n_vars, p->d_zt.p, p->d_z.p);
             if ((rc = fetch_state(p))) return rc;
             prof_mark(p, 6);
             CU(cudaGetLastError());
             p->total_tries++;
             gain = p->h_st->gain;
             accepted = p->h_st->accepted != 0;
-            if (accepted) { std::swap(p->d_z.p, p->d_zt.p); p->cost = p->h_st->cost; p->huber_eval = p->huber_cur; }
+            if (accepted) { p->cost = p->h_st->cost; p->huber_eval = p->huber_cur; }
             if (p->profiling) {
                 cudaEventSynchronize(p->ev[6]);
                 float ms;

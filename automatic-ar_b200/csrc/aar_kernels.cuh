@@ -13,6 +13,21 @@ constexpr int POSE_STRIDE = 12;
 constexpr int FC_STRIDE_K = 28;  // per frame: packed lower Cholesky factor of Hff + mu I (21) | y = L^-1 Bf (6) | pad  (aar_schur.cuh: FC_STRIDE)
 
 // Everything the kernels need, by value.
+// ---------------------------------------------------------------------------------------------
+// LM state, device resident (sparselevmarq.h:130-135, 237-249).
+struct LmState {
+    double cost, prev_cost, trial_cost, mu, v, gain, L;
+    double maxdiag;          // local max diagonal of JtJ (first iteration)
+    float huber_delta, huber_eval;   // hubberDelta of the next evaluation / the one the accepted iterate was evaluated with (multicam_mapper.cpp:412-417)
+    int accepted, tries, iter, exit_code, chol_fail, pad;
+    // ---- control block of the graph-resident loop (aar_lm_iterate: SparseLevMarq::solve, sparselevmarq.h:439-472, without a host in it)
+    int iters_done, max_iters, must_exit /* 0 run | 1..3 stop rules | -1 numeric | -2 hand back to the host loop */, ignore_stop;
+    double min_error, min_step, min_avg, rows;
+    long long total_tries;
+    int trace_cap, trace_len;
+};
+struct LmTraceDev { double cost, mu, gain; int tries, accepted; float huber_delta; int pad; };   // == aar_lm_trace (include/aar_cuda.h)
+
 struct DevProblem {
     int C, M, F;                 // cameras, markers, LOCAL frames (this rank's shard)
     long long N;                 // local observations
@@ -33,6 +48,7 @@ struct DevProblem {
     const float4 *und_a, *und_b, *raw_a, *raw_b; // x0 y0 x1 y1 | x2 y2 x3 y3
     double *intr;                // [C][4] fx cx fy cy at z (constant unless the intrinsics are optimised: then written by k_expand_intr)
     double *intr_tr;             // the same at the trial point (k_residual); == intr when the intrinsics are fixed
+    const LmState *st_dev;       // graph-resident loop: the Huber delta comes from the device state instead of the launch parameter (null otherwise)
     int opt_i, nri, col_intr0;   // intrinsics optimised; 2 C pseudo-blocks behind the pose blocks; their first column in the internal z (aar_intrinsics.cuh)
     // frame CSR of W slots: per frame the camera blocks seen (in order of first appearance), then the marker blocks
     const int *frame_slot_ptr;   // [F+1]
@@ -141,6 +157,7 @@ __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam
                            const double *__restrict__ fr, int fr_stride, float huber_delta, double *__restrict__ r_out, double *__restrict__ cost) {
     long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0;
+    if (p.st_dev) huber_delta = p.st_dev->huber_delta;
     if (o < p.N) {
         int cm = p.obs_cm[o], f = p.obs_f[o], c = obs_cam(cm), m = obs_marker(cm);
         Intr k; k.fx = p.intr_tr[4 * c]; k.cx = p.intr_tr[4 * c + 1]; k.fy = p.intr_tr[4 * c + 2]; k.cy = p.intr_tr[4 * c + 3];
@@ -182,14 +199,6 @@ __global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// LM state, device resident (sparselevmarq.h:130-135, 237-249).
-struct LmState {
-    double cost, prev_cost, trial_cost, mu, v, gain, L;
-    double maxdiag;          // local max diagonal of JtJ (first iteration)
-    float huber_delta, huber_eval;
-    int accepted, tries, iter, exit_code, chol_fail, pad;
-};
 
 // 6x6 Cholesky of packed-upper H + mu I, lower factor L (row-major 6x6, only i>=j used). Returns false on a non-positive pivot.
 __device__ __forceinline__ bool chol6(const double *hf, double mu, double *L) {
@@ -361,6 +370,66 @@ __global__ void k_lm_decide(LmState *st, const double *__restrict__ red, int n_r
         st->accepted = 1;
     } else { st->mu = mu * st->v; st->v = st->v * 5; }
     st->tries += 1;
+}
+
+// ---- the same decisions without a host in the loop: CUDA-graph WHILE nodes whose conditions these kernels set -------------
+// start of an iteration (after J^T J): mu0 never needs computing here (the first iteration runs on the host path); an inexact
+// float32 staging (flags[1]) hands the iteration back to the host loop before any step is tried
+__global__ void k_lm_begin_iter_g(LmState *st, const int *__restrict__ flags, cudaGraphConditionalHandle inner) {
+    if (threadIdx.x || blockIdx.x) return;
+    st->tries = 0; st->accepted = 0; st->gain = 0;
+    const bool hand_back = flags[1] != 0;
+    if (hand_back) st->must_exit = -2;
+    cudaGraphSetConditional(inner, hand_back ? 0u : 1u);
+}
+// after a try: gain / accept / reject as k_lm_decide, then the do-while condition of sparselevmarq.h:384-419
+__global__ void k_lm_decide_g(LmState *st, const double *__restrict__ red, int n_r, const double *__restrict__ dr, const double *__restrict__ Br, cudaGraphConditionalHandle inner) {
+    if (threadIdx.x || blockIdx.x) return;
+    double dd = red[1], dB = red[2];
+    for (int i = 0; i < n_r; i++) { dd = fma(dr[i], dr[i], dd); dB = fma(dr[i], Br[i], dB); }
+    const double err = red[0], mu = st->mu;
+    const double L = 0.5 * (mu * dd - dB);
+    const double gain = (err - st->prev_cost) / L;
+    st->L = L; st->gain = gain; st->trial_cost = err;
+    if (gain > 0 && ((err - st->prev_cost) < 0)) {
+        double t = 2 * gain - 1;
+        st->mu = mu * fmax(0.33, 1. - t * t * t);
+        st->v = 2.;
+        st->cost = err;
+        st->accepted = 1;
+        st->huber_eval = st->huber_delta;
+    } else { st->mu = mu * st->v; st->v = st->v * 5; }
+    st->tries += 1; st->total_tries += 1;
+    cudaGraphSetConditional(inner, (gain <= 0 && st->tries <= 5 && !st->accepted) ? 1u : 0u);
+}
+// accepted trial point becomes the iterate (the host path swaps two pointers instead)
+__global__ void k_lm_commit(const LmState *__restrict__ st, long long n, const double *__restrict__ zt, double *__restrict__ z) {
+    if (!st->accepted) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) z[i] = zt[i];
+}
+// end of an iteration: stop rules of SparseLevMarq::solve (sparselevmarq.h:453-465), trace, step callback (hubberDelta annealing)
+__global__ void k_lm_iter_end_g(LmState *st, int *__restrict__ flags, LmTraceDev *__restrict__ trace, cudaGraphConditionalHandle outer) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (st->must_exit == -2) { cudaGraphSetConditional(outer, 0u); return; }
+    const double currErr = st->cost, prevErr = st->prev_cost;
+    int mustExit = 0;
+    if (!(st->trial_cost - st->trial_cost == 0.0) || flags[0] || flags[2]) mustExit = -1;      // non-finite cost, non-positive pivot, camera table assumption
+    else if (!st->ignore_stop) {
+        if (currErr < st->min_error) mustExit = 1;
+        if (fabs(prevErr - currErr) <= st->min_step || fabs((prevErr - currErr) / st->rows) <= st->min_avg || !st->accepted) mustExit = 2;
+        if (currErr > prevErr) mustExit = 3;
+    }
+    if (mustExit >= 0 && st->trace_len < st->trace_cap) {
+        LmTraceDev &t = trace[st->trace_len++];
+        t.cost = currErr; t.mu = st->mu; t.gain = st->gain; t.tries = st->tries; t.accepted = st->accepted; t.huber_delta = st->huber_delta; t.pad = 0;
+    }
+    if (mustExit >= 0) {
+        if (st->huber_delta > 2.5f) st->huber_delta = (float)((double)st->huber_delta - 7.5 / 500);
+        st->prev_cost = currErr; st->cost = currErr;
+        st->iters_done += 1;
+    }
+    st->must_exit = mustExit;
+    cudaGraphSetConditional(outer, (mustExit == 0 && st->iters_done < st->max_iters) ? 1u : 0u);
 }
 
 // one-off device undistortion pass — cv::undistortPoints(..., K, dist, noArray, K) as called by
