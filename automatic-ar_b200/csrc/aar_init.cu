@@ -201,38 +201,42 @@ inline bool kept_position(long long pos, long long n, long long k) {
 // Pass 1 counts the candidates of every (id1, id2), pass 2 records the kept ones: src = (2 * det_a + cand_a, 2 * det_b + cand_b).
 int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) {
     typedef std::pair<int, int> Key;
-    std::map<Key, long long> count, seen;
-    std::map<Key, std::vector<int2>> lists;
-    std::vector<std::pair<std::pair<int, int>, long long>> members;          // ((group id, member id), detection) of one frame
+    // member ids -> ranks (cameras: the id; markers: rank among the marker ids), pair (rank1, rank2) -> dense table index
+    const int K = cams ? h->num_cams : (int)h->marker_list.size();
+    if ((long long)K * K > (1LL << 26)) { ierr("too many %s (%d) for the pair tables of the rig initialisation", cams ? "cameras" : "markers", K); return AAR_ERR_UNSUPPORTED; }
+    auto rank_of_member = [&](int id) { return cams ? id : (int)(std::lower_bound(h->marker_list.begin(), h->marker_list.end(), id) - h->marker_list.begin()); };
+    std::vector<long long> count((size_t)K * K, 0), seen((size_t)K * K, 0);
+    std::vector<std::vector<int2>> lists((size_t)K * K);
+    struct Mem { int group, member_rank; long long det; };
+    std::vector<Mem> members;
     for (int pass = 0; pass < 2; pass++) {
         for (int f = 0; f < h->num_frames; f++) {
             if (!h->frame_kept[f]) continue;
             members.clear();
             for (long long d = h->frame_first[f]; d < h->frame_first[f + 1]; d++)
-                if (h->ncand[d]) members.push_back({cams ? std::make_pair(h->det_marker[d], h->det_cam[d]) : std::make_pair(h->det_cam[d], h->det_marker[d]), d});
-            std::stable_sort(members.begin(), members.end(), [](const std::pair<std::pair<int, int>, long long> &a, const std::pair<std::pair<int, int>, long long> &b) { return a.first < b.first; });
+                if (h->ncand[d]) members.push_back(cams ? Mem{h->det_marker[d], h->det_cam[d], d} : Mem{h->det_cam[d], rank_of_member(h->det_marker[d]), d});
+            std::stable_sort(members.begin(), members.end(), [](const Mem &a, const Mem &b) { return a.group != b.group ? a.group < b.group : a.member_rank < b.member_rank; });
             size_t g0 = 0;
             while (g0 < members.size()) {
                 size_t g1 = g0;
-                while (g1 < members.size() && members[g1].first.first == members[g0].first.first) g1++;
+                while (g1 < members.size() && members[g1].group == members[g0].group) g1++;
                 // members of the group [g0, g1) ascending by id; distinct ids = the reference's `objects` map
-                if (members[g1 - 1].first.second != members[g0].first.second)
+                if (members[g1 - 1].member_rank != members[g0].member_rank)
                     for (size_t a0 = g0; a0 < g1;) {
-                        size_t a1 = a0; while (a1 < g1 && members[a1].first.second == members[a0].first.second) a1++;
-                        const int id1 = members[a0].first.second;
+                        size_t a1 = a0; while (a1 < g1 && members[a1].member_rank == members[a0].member_rank) a1++;
+                        const size_t row = (size_t)members[a0].member_rank * K;
                         for (size_t a = a0; a < a1; a++)
-                            for (int i = 0; i < h->ncand[members[a].second]; i++)
+                            for (int i = 0; i < h->ncand[members[a].det]; i++)
                                 for (size_t b = a1; b < g1; b++) {
-                                    const int id2 = members[b].first.second;
-                                    const Key key(id1, id2);
-                                    const int nb = h->ncand[members[b].second];
+                                    const size_t key = row + (size_t)members[b].member_rank;
+                                    const int nb = h->ncand[members[b].det];
                                     if (pass == 0) count[key] += nb;
                                     else {
                                         long long &pos = seen[key];
                                         const long long n = count[key];
                                         for (int j = 0; j < nb; j++, pos++)
                                             if (kept_position(pos, n, h->consensus_max))
-                                                lists[key].push_back(make_int2((int)(2 * members[a].second + i), (int)(2 * members[b].second + j)));
+                                                lists[key].push_back(make_int2((int)(2 * members[a].det + i), (int)(2 * members[b].det + j)));
                                     }
                                 }
                         a0 = a1;
@@ -240,9 +244,16 @@ int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) 
                 g0 = g1;
             }
         }
+        if (pass == 0 && h->consensus_max > 0) for (size_t k = 0; k < lists.size(); k++) if (count[k]) lists[k].reserve((size_t)std::min<long long>(count[k], h->consensus_max));
     }
-    std::vector<int2> src; std::vector<long long> seg_begin(1, 0); std::vector<Key> keys;
-    for (auto &kv : lists) { src.insert(src.end(), kv.second.begin(), kv.second.end()); seg_begin.push_back((long long)src.size()); keys.push_back(kv.first); }
+    std::vector<int2> src; std::vector<long long> seg_begin(1, 0), seg_count; std::vector<Key> keys;
+    for (int r1 = 0; r1 < K; r1++)                              // (id1, id2) ascending: the iteration order of the reference's nested maps
+        for (int r2 = 0; r2 < K; r2++) {
+            const size_t k = (size_t)r1 * K + r2;
+            if (lists[k].empty()) continue;
+            src.insert(src.end(), lists[k].begin(), lists[k].end()); seg_begin.push_back((long long)src.size()); seg_count.push_back(count[k]);
+            keys.push_back(cams ? Key(r1, r2) : Key(h->marker_list[(size_t)r1], h->marker_list[(size_t)r2]));
+        }
     if (src.empty()) return AAR_OK;
     DevBuf<int2> d_src; DevBuf<double> tri;
     ICU(d_src.upload(src, h->stream)); ICU(tri.alloc(src.size() * TRI_DOUBLES));
@@ -254,7 +265,7 @@ int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) 
     for (size_t s = 0; s < keys.size(); s++) {
         if (bi[s] < 0) { ierr("consensus of (%d, %d) has no finite candidate", keys[s].first, keys[s].second); return AAR_ERR_NUMERIC; }
         best[keys[s].first][keys[s].second] = std::make_pair(h4_from12(&bt[12 * s]), w[s]);
-        edges.push_back(Edge{keys[s].first, keys[s].second, count[keys[s]], w[s]});
+        edges.push_back(Edge{keys[s].first, keys[s].second, seg_count[s], w[s]});
     }
     return AAR_OK;
 }
@@ -308,12 +319,21 @@ int aar_init_create(const aar_init_desc *d, aar_init **out) {
         if (!(num >= h->min_detections)) continue;
         h->frame_kept[f] = 1;
         for (long long i = h->frame_first[f]; i < h->frame_first[f + 1]; i++)
-            if (!(d->excluded_cams && d->excluded_cams[h->det_cam[i]])) { h->active[i] = 1; h->cam_ids.insert(h->det_cam[i]); h->marker_ids.insert(h->det_marker[i]); }
+            if (!(d->excluded_cams && d->excluded_cams[h->det_cam[i]])) h->active[i] = 1;
+    }
+    {   // get_cam_ids / get_marker_ids: one pass over the active detections (a std::set insert per detection dominated cfg 4)
+        std::vector<uint8_t> cam_seen((size_t)h->num_cams, 0);
+        std::vector<int> mk; mk.reserve(1024);
+        int last_marker = INT32_MIN;
+        for (long long i = 0; i < N; i++)
+            if (h->active[i]) { cam_seen[(size_t)h->det_cam[i]] = 1; const int m = h->det_marker[i]; if (m != last_marker) { mk.push_back(m); last_marker = m; if (mk.size() >= (1u << 20)) { std::sort(mk.begin(), mk.end()); mk.erase(std::unique(mk.begin(), mk.end()), mk.end()); } } }
+        for (int c = 0; c < h->num_cams; c++) if (cam_seen[(size_t)c]) h->cam_ids.insert(c);
+        h->marker_ids.insert(mk.begin(), mk.end());
     }
     h->marker_list.assign(h->marker_ids.begin(), h->marker_ids.end());
     for (size_t i = 0; i < h->marker_list.size(); i++) h->marker_rank[h->marker_list[i]] = (int)i;
     std::vector<int> midx(N, 0);
-    for (long long i = 0; i < N; i++) if (h->active[i]) midx[i] = h->marker_rank[h->det_marker[i]];
+    for (long long i = 0; i < N; i++) if (h->active[i]) midx[i] = (int)(std::lower_bound(h->marker_list.begin(), h->marker_list.end(), h->det_marker[i]) - h->marker_list.begin());
 
     ICU(cudaSetDevice(h->device));
     if (d->stream) h->stream = (cudaStream_t)d->stream; else { ICU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
