@@ -153,7 +153,10 @@ namespace aar {
 
 // eval_curr_solution (mcm.cpp:996-1028): residuals of every observation + sum of squares.
 // cam/mk/fr: base pose tables with the given strides (trial tables or variant-0 of the Jacobian tables).
-__global__ void k_residual(DevProblem p, const double *__restrict__ cam, int cam_stride, const double *__restrict__ mk, int mk_stride,
+#ifndef AAR_RES_MINBLOCKS
+#define AAR_RES_MINBLOCKS 3         // measured at cfg 4 (20 k frames): 231 us at 94 registers / 2 CTAs per SM, 184 us at 3 CTAs (a few spilled bytes), 191 us at 4
+#endif
+__global__ void __launch_bounds__(256, AAR_RES_MINBLOCKS) k_residual(DevProblem p, const double *__restrict__ cam, int cam_stride, const double *__restrict__ mk, int mk_stride,
                            const double *__restrict__ fr, int fr_stride, float huber_delta, double *__restrict__ r_out, double *__restrict__ cost) {
     long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0;
@@ -256,7 +259,10 @@ __device__ __forceinline__ void bwd6(const double *L, double *x) {
 // the frame's W slots (consecutive 288-byte blocks -> coalesced), the 6 partial sums meet by shuffles, lane 0 finishes with
 // the factor L and y = L^-1 B that k_frame_chol left in `fc`:  delta_f = L^-T (y - L^-1 sum_s W_s^T delta_r[s]).
 constexpr int BS_WARPS = 8;
-__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevProblem p, const double *__restrict__ fc, const double *__restrict__ Hf, const double *__restrict__ W,
+#ifndef AAR_BS_MINBLOCKS
+#define AAR_BS_MINBLOCKS 4          // measured at cfg 4 (20 k frames): 139 us with 2 CTAs per SM, 130 us with 4
+#endif
+__global__ void __launch_bounds__(BS_WARPS * 32, AAR_BS_MINBLOCKS) k_backsub(DevProblem p, const double *__restrict__ fc, const double *__restrict__ Hf, const double *__restrict__ W,
                                                            const double *__restrict__ dr, const double *__restrict__ z, double *__restrict__ zt, double *__restrict__ red3) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double dd = 0, dB = 0;

@@ -43,7 +43,10 @@ __global__ void k_frame_chol(DevProblem p, const LmState *__restrict__ st, const
 
 // One thread per W slot: E_s[i][:] = L^-1 W_s[i][:]^T for its six rows (the 27 doubles of the frame's factor are read once
 // per slot, the slot itself with 16-byte loads / stores), and b[blk(s)] -= E_s y.
-__global__ void __launch_bounds__(256) k_schur_prepare(DevProblem p, long long nslots, const int *__restrict__ slot_frame, const double *__restrict__ fc,
+#ifndef AAR_SP_MINBLOCKS
+#define AAR_SP_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, AAR_SP_MINBLOCKS) k_schur_prepare(DevProblem p, long long nslots, const int *__restrict__ slot_frame, const double *__restrict__ fc,
                                                        const double *__restrict__ W, double *__restrict__ E, double *__restrict__ b) {
     extern __shared__ double sb[];   // [n_r] partial b of this CTA
     for (int i = threadIdx.x; i < p.n_r; i += blockDim.x) sb[i] = 0.0;
