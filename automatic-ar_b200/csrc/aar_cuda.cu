@@ -124,7 +124,7 @@ struct aar_problem {
     // ---- comm
     ncclComm_t comm = nullptr;
     // ---- instrumentation
-    long long launches = 0; bool profiling = false;
+    long long launches = 0; bool profiling = false; bool exact_next = false;   // exact_next: redo this Jacobian with FP64 staging
     // graph-resident LM loop (aar_lm_iterate): two nested WHILE nodes, conditions set by k_lm_decide_g / k_lm_iter_end_g
     cudaGraph_t lm_graph = nullptr; cudaGraphExec_t lm_exec = nullptr; cudaGraphConditionalHandle lm_outer = 0, lm_inner = 0; cudaStream_t lm_side = nullptr;
     bool lm_graph_tried = false, lm_graph_ok = false, capturing = false; long long lm_graph_launches = 0, lm_graph_iters = 0; int lm_body_launches = 0, lm_try_launches = 0;
@@ -287,7 +287,7 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
 
 // J^T J blocks and J^T r at d_z (sparselevmarq.h:353-367) into Hf / W / Hrr / gr; or the dense per-observation
 // Jacobian blocks into Jdump (parity hook)
-int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
+int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump, bool defer_check = false) {
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
     if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, p->d_z.p, p->d_intr.p);
@@ -299,7 +299,7 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
     }
     const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
-        const bool exact = p->force_exact_staging || attempt == 1;
+        const bool exact = p->force_exact_staging || attempt == 1 || p->exact_next;
         if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
         if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
         if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
@@ -312,7 +312,10 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump) {
         if (exact) { if (p->d_Jn64.n < JROW * Np) CU(p->d_Jn64.alloc(JROW * Np)); rc = launch_jacobian<double>(p, huber_eval, p->d_Jn64.p); }
         else { if (p->d_Jn32.n < JROW * Np) CU(p->d_Jn32.alloc(JROW * Np)); rc = launch_jacobian<float>(p, huber_eval, p->d_Jn32.p); }
         if (rc) return rc;
-        if (exact || p->capturing) break;      // graph-resident loop: k_lm_begin_iter_g looks at the flag on the device and hands the iteration back
+        if (exact) { p->exact_next = false; break; }
+        // graph-resident loop: k_lm_begin_iter_g looks at the flag on the device and hands the iteration back; host-driven LM loop: k_lm_decide
+        // refuses the step of an inexact staging and the flag arrives with the state of the try (no synchronisation of its own)
+        if (p->capturing || defer_check) break;
         // the float32 staging of the numerators is exact unless the kernel says otherwise (never seen on real data)
         CU(cudaMemcpyAsync(p->h_flags, p->d_flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
@@ -388,6 +391,7 @@ int build_and_solve_reduced(aar_problem *p) {
 
 int fetch_state(aar_problem *p) {
     CU(cudaMemcpyAsync(p->h_st, p->d_st.p, sizeof(LmState), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_flags, p->d_flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));   // rides on the same synchronisation
     CU(cudaStreamSynchronize(p->stream));
     return AAR_OK;
 }
@@ -1164,7 +1168,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
         // ---- J, JtJ blocks, B (sparselevmarq.h:353-367)
         prof_mark(p, 0);
         if ((rc = zero_normal_equations(p))) return rc;
-        if ((rc = jacobian_accumulate(p, p->huber_eval, nullptr))) { p->lm_active = false; return rc; }
+        if ((rc = jacobian_accumulate(p, p->huber_eval, nullptr, true))) { p->lm_active = false; return rc; }
         prof_mark(p, 1);
         if (p->h_st->mu < 0) { // first iteration: mu = tau * max diag(JtJ) (sparselevmarq.h:369-377)
             p->h_st->maxdiag = -1e300; push_state(p);
@@ -1195,12 +1199,13 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             residual(p, p->d_zt.p, p->huber_cur, nullptr);
             prof_mark(p, 5);
             if ((rc = allreduce(p, p->d_red3.p, 3, ncclSum))) return rc;
-            LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br);
+            LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->d_flag.p);
             // an accepted trial point becomes the iterate by a device copy (a pointer swap would invalidate the captured graph of the resident loop)
             LAUNCH(p, k_lm_commit, std::max(1, std::min(2 * p->num_sms, (int)cdiv(p->n_vars, 256))), 256, 0, p->d_st.p, p->n_vars, p->d_zt.p, p->d_z.p);
             if ((rc = fetch_state(p))) return rc;
             prof_mark(p, 6);
             CU(cudaGetLastError());
+            if (p->h_st->must_exit == -2) break;          // inexact float32 staging: nothing was decided, the iteration is redone below
             p->total_tries++;
             gain = p->h_st->gain;
             accepted = p->h_st->accepted != 0;
@@ -1221,9 +1226,14 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
                 cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]); p->phase_ms[4] += ms;
             }
         } while (gain <= 0 && ntries++ < 5 && !accepted);
-        int flags[4];
-        CU(cudaMemcpyAsync(flags, p->d_flag.p, sizeof flags, cudaMemcpyDeviceToHost, p->stream));
-        CU(cudaStreamSynchronize(p->stream));
+        if (p->h_st->must_exit == -2) {                   // redo this iteration with FP64 staging of the numerators (never seen on real data)
+            p->exact_reruns++; p->exact_next = true;
+            p->h_st->must_exit = 0;
+            CU(cudaMemsetAsync(p->d_flag.p + 1, 0, sizeof(int), p->stream));
+            if ((rc = push_state(p))) return rc;
+            it--; continue;
+        }
+        const int *flags = p->h_flags;                    // fetched with the state of the last try
         if (!std::isfinite(p->h_st->trial_cost)) { set_err("non-finite cost at iteration %d", p->iter); p->lm_active = false; return AAR_ERR_NUMERIC; }
         if (flags[0] || flags[2]) {
             // flags[0]: a non-positive pivot in a frame block or in the reduced system (the kernels substituted 1 to keep going):

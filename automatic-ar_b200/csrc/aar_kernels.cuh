@@ -360,8 +360,9 @@ __global__ void k_lm_begin_iter(LmState *st, int n_r, const double *__restrict__
 }
 // gain / accept / reject (sparselevmarq.h:402-419). red = [trial_cost, dd_f, dB_f] (all-reduced);
 // delta_r.delta_r and delta_r.Br are added here (identical on every rank).
-__global__ void k_lm_decide(LmState *st, const double *__restrict__ red, int n_r, const double *__restrict__ dr, const double *__restrict__ Br) {
+__global__ void k_lm_decide(LmState *st, const double *__restrict__ red, int n_r, const double *__restrict__ dr, const double *__restrict__ Br, const int *__restrict__ flags) {
     if (threadIdx.x || blockIdx.x) return;
+    if (flags[1]) { st->must_exit = -2; st->accepted = 0; return; }      // inexact float32 staging of this Jacobian: decide nothing, the host redoes the iteration
     double dd = red[1], dB = red[2];
     for (int i = 0; i < n_r; i++) { dd = fma(dr[i], dr[i], dd); dB = fma(dr[i], Br[i], dB); }
     const double err = red[0], mu = st->mu;
