@@ -152,6 +152,7 @@ int rank_of(const std::vector<int> &ids, int id) {
 }
 
 // ---- host-side parallel loops of aar_problem_create (plain std::thread: the library links nothing but the CUDA runtime)
+thread_local int g_ranks_on_host = 1;     // ranks of a sharded run that map their shards at the same time on this host (set by aar_problem_create)
 int host_threads(long long work) {
     if (work < (1LL << 16)) return 1;
     static int n = [] {
@@ -161,7 +162,7 @@ int host_threads(long long work) {
         int c = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
         return std::max(1, std::min(c, 64));
     }();
-    return n;
+    return std::max(1, n / std::max(1, g_ranks_on_host));     // one process per GPU: the ranks share the cores (8 x 64 threads took 4.0 s where one rank takes 1.2 s)
 }
 template <class F> void parallel_for(long long n, int T, F fn) {      // fn(begin, end, thread index) over T contiguous chunks of [0, n)
     if (T <= 1 || n <= 0) { fn(0, std::max<long long>(n, 0), 0); return; }
@@ -343,7 +344,7 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
     LAUNCH(p, k_frame_chol, cdiv(F, 128), 128, 0, p->dp, p->d_st.p, p->d_Hf.p, p->d_fc.p, p->d_flag.p);      // also feeds k_backsub
     if (n_r > 0 && p->nslots > 0) {
         const int g1 = (int)std::max<long long>(1, std::min<long long>(4LL * p->num_sms, (p->nslots + 255) / 256));
-        LAUNCH(p, k_schur_prepare, g1, 256, (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
+        LAUNCH(p, k_schur_prepare, g1, 256, 8 * SP_TILE_BYTES + (size_t)n_r * sizeof(double), p->dp, p->nslots, p->d_slot_frame.p, p->d_fc.p, p->d_W.p, p->d_E.p, b);
         const int tiles_side = (nb + SY_TB - 1) / SY_TB, ntiles = tiles_side * (tiles_side + 1) / 2;
         // two CTAs per SM, at most two full waves (no tail wave), at least a few pipeline stages per CTA
         const int nchunks = std::max(1, std::min((2 * AAR_SY_MINBLOCKS * p->num_sms) / ntiles, (F + 4 * SY_FB - 1) / (4 * SY_FB)));
@@ -444,6 +445,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     p->J_delta = d->J_delta > 0 ? d->J_delta : 1e-3;
     p->device = d->device; p->rank = d->world_size > 1 ? d->rank : 0; p->world = d->world_size > 1 ? d->world_size : 1;
     if (p->rank < 0 || p->rank >= p->world) { set_err("bad rank"); return AAR_ERR_INVALID; }
+    g_ranks_on_host = std::max(1, d->world_size);
     p->opt_i = d->optimize_cam_intrinsics != 0;
     p->nrc = p->opt_c ? p->C - 1 : 0; p->nrm = p->opt_m ? p->M - 1 : 0; p->nri = p->opt_i ? 2 * p->C : 0; p->n_r = 6 * (p->nrc + p->nrm + p->nri);
     p->n_vars = p->n_r + (p->opt_f ? 6LL * p->F : 0);
@@ -726,7 +728,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         else if (cudaFuncSetAttribute(k_reduced_solve_cluster2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
                  cudaFuncSetAttribute(k_reduced_solve_cluster2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); p->use_cluster_solve = false; }
     }
-    if ((size_t)p->n_r * sizeof(double) > 48 * 1024) CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)p->n_r * sizeof(double))));
+    CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SP_TILE_BYTES + (size_t)p->n_r * sizeof(double))));
     CU(cudaStreamSynchronize(p->stream));
     aar_lm_default_params(&p->params);
     guard.release();

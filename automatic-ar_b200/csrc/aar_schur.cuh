@@ -41,43 +41,71 @@ __global__ void k_frame_chol(DevProblem p, const LmState *__restrict__ st, const
     for (int i = 0; i < 6; i++) dst[21 + i] = y[i];
 }
 
-// One thread per W slot: E_s[i][:] = L^-1 W_s[i][:]^T for its six rows (the 27 doubles of the frame's factor are read once
-// per slot, the slot itself with 16-byte loads / stores), and b[blk(s)] -= E_s y.
+// One thread per W slot: E_s[i][:] = L^-1 W_s[i][:]^T for its six rows, and b[blk(s)] -= E_s y.  The 32 slots of a warp are 9216
+// consecutive bytes: they come in and go out through a per-warp shared-memory tile with coalesced 16-byte accesses (one thread
+// walking its own 288-byte slot left half of every 32-byte sector unused per instruction: 3.4 TB/s at cfg 4); the 27 doubles of
+// the frame's factor are read once per slot (neighbouring lanes share frames: L1 hits).
+constexpr int SP_LD = 38;                                  // padded slot stride in shared memory (16-byte aligned, conflict-free for lane = slot)
+constexpr size_t SP_TILE_BYTES = 32 * SP_LD * sizeof(double);
 #ifndef AAR_SP_MINBLOCKS
 #define AAR_SP_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(256, AAR_SP_MINBLOCKS) k_schur_prepare(DevProblem p, long long nslots, const int *__restrict__ slot_frame, const double *__restrict__ fc,
-                                                       const double *__restrict__ W, double *__restrict__ E, double *__restrict__ b) {
-    extern __shared__ double sb[];   // [n_r] partial b of this CTA
+                                                                         const double *__restrict__ W, double *__restrict__ E, double *__restrict__ b) {
+    extern __shared__ __align__(16) double sp_smem[];   // [8 warps][32][SP_LD] tiles | [n_r] partial b of this CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *tile = sp_smem + (size_t)warp * 32 * SP_LD;
+    double *sb = sp_smem + (size_t)8 * 32 * SP_LD;
     for (int i = threadIdx.x; i < p.n_r; i += blockDim.x) sb[i] = 0.0;
     __syncthreads();
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
-        const double *lf = fc + (size_t)slot_frame[s] * FC_STRIDE;
-        double l[27];
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long s0 = ((long long)blockIdx.x * 8 + warp) * 32; s0 < nslots; s0 += nwarps * 32) {
+        const int ns = (int)min(32LL, nslots - s0);
+        // ---- 32 slots in: lane l takes double2 number l, l + 32, ... of the 18 * ns of the tile
+        const double2 *src = reinterpret_cast<const double2 *>(W + (size_t)s0 * 36);
 #pragma unroll
-        for (int i = 0; i < 27; i++) l[i] = lf[i];
-        const double2 *w2 = reinterpret_cast<const double2 *>(W + (size_t)s * 36);
-        double2 *e2 = reinterpret_cast<double2 *>(E + (size_t)s * 36);
-        double *bs = sb + 6 * p.slot_block[s];
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            double x[6];
-#pragma unroll
-            for (int k = 0; k < 3; k++) { const double2 v = w2[i * 3 + k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
-            int idx = 0; double acc = 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; r++) {            // forward substitution with the packed lower factor
-                double v = x[r];
-#pragma unroll
-                for (int k = 0; k < r; k++) v = fma(-l[idx + k], x[k], v);
-                x[r] = v / l[idx + r];
-                idx += r + 1;
-                acc = fma(x[r], l[21 + r], acc);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) e2[i * 3 + k] = make_double2(x[2 * k], x[2 * k + 1]);
-            atomicAdd(bs + i, -acc);
+        for (int k = 0; k < 18; k++) {
+            const int e = lane + 32 * k;
+            if (e < 18 * ns) { const double2 v = src[e]; *reinterpret_cast<double2 *>(tile + (e / 18) * SP_LD + 2 * (e % 18)) = v; }
         }
+        __syncwarp();
+        if (lane < ns) {
+            const long long s = s0 + lane;
+            const double *lf = fc + (size_t)slot_frame[s] * FC_STRIDE;
+            double l[27];
+#pragma unroll
+            for (int i = 0; i < 27; i++) l[i] = lf[i];
+            double *w = tile + lane * SP_LD;
+            double *bs = sb + 6 * p.slot_block[s];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double x[6];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double2 v = *reinterpret_cast<const double2 *>(w + i * 6 + 2 * k); x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                int idx = 0; double acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {            // forward substitution with the packed lower factor
+                    double v = x[r];
+#pragma unroll
+                    for (int k = 0; k < r; k++) v = fma(-l[idx + k], x[k], v);
+                    x[r] = v / l[idx + r];
+                    idx += r + 1;
+                    acc = fma(x[r], l[21 + r], acc);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) *reinterpret_cast<double2 *>(w + i * 6 + 2 * k) = make_double2(x[2 * k], x[2 * k + 1]);
+                atomicAdd(bs + i, -acc);
+            }
+        }
+        __syncwarp();
+        // ---- 32 slots out
+        double2 *dst = reinterpret_cast<double2 *>(E + (size_t)s0 * 36);
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+            const int e = lane + 32 * k;
+            if (e < 18 * ns) dst[e] = *reinterpret_cast<const double2 *>(tile + (e / 18) * SP_LD + 2 * (e % 18));
+        }
+        __syncwarp();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.n_r; i += blockDim.x) if (sb[i] != 0.0) atomicAdd(b + i, sb[i]);

@@ -450,3 +450,33 @@ def test_intrinsics_block_lm_steps_and_solve(binding, oracle_mod):
     parity_record("intrinsics_block_lm_vs_reference_solver", first_steps_worst_rel_dev=worst, iterations=[int(it_g), int(it_o)], final_cost=[float(c_g), float(c_o)],
                   rel_dev_final_cost=d_cost, ref_envelope_cost=env_c, north_star=1e-6)
     _end_point_bar(d_cost, env_c, 2e-5)
+
+
+def test_graph_resident_loop_equals_host_driven_loop(binding, oracle_mod, monkeypatch):
+    """aar_lm_iterate runs SparseLevMarq::solve as nested CUDA-graph WHILE nodes (decisions on the device); AAR_NO_GRAPH=1 keeps the
+    host-driven loop (one read-back per try).  Same kernels in the same order: iteration and try counts must be identical and
+    iterates, costs and damping equal up to the order of the atomic sums of the assembly (two runs of the SAME loop differ in the last
+    bits too), with and without Huber (the hubberDelta annealing lives in the device state)."""
+    def same(a, b, tol=1e-9):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return a.shape == b.shape and np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300)
+    for name, huber in (("cfg1", False), ("cfg2", False), ("cfg1", True)):
+        rig = synth.make_config(name)
+        p = binding.Problem(rig, with_huber=huber)
+        z0 = p.mats2evec()
+        monkeypatch.setenv("AAR_NO_GRAPH", "1")
+        z_h, c_h, it_h, tr_h = p.solve(z0)
+        monkeypatch.delenv("AAR_NO_GRAPH")
+        l0 = p.kernel_launches
+        z_g, c_g, it_g, tr_g = p.solve(z0)
+        assert it_g == it_h and same(c_g, c_h, 1e-12) and same(z_g, z_h), (name, huber, it_g, it_h, c_g, c_h)
+        assert np.array_equal(tr_g[:, 3:5], tr_h[:, 3:5]) and same(tr_g[:, 0], tr_h[:, 0]) and same(tr_g[:, 1], tr_h[:, 1], 1e-7) and np.array_equal(tr_g[:, 5], tr_h[:, 5])
+        assert p.kernel_launches > l0
+        # a capped number of iterations and the stop rules switched off (the bench's mode)
+        prm = binding.Problem.default_params(max_iters=7, ignore_stop_rules=1)
+        monkeypatch.setenv("AAR_NO_GRAPH", "1")
+        z_h, c_h, it_h, tr_h = p.solve(z0, prm)
+        monkeypatch.delenv("AAR_NO_GRAPH")
+        z_g, c_g, it_g, tr_g = p.solve(z0, prm)
+        assert it_g == it_h == 7 and same(c_g, c_h, 1e-12) and same(z_g, z_h) and np.array_equal(tr_g[:, 3:6], tr_h[:, 3:6])
+    parity_record("graph_resident_loop_vs_host_driven_loop", same_iterations_tries_huber=True, rel_tol_z=1e-9, workloads=["cfg1", "cfg2", "cfg1 + Huber"])
