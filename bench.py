@@ -475,7 +475,9 @@ def run_ours(args, rank, world, local_rank):
                     "peak_source": peaks["fp64_src"], "ms_per_launch": ms_launch, "share_of_step": ms_launch * (1 if "syrk" not in kernel else ph["syrk_launches"] / nl) / (ms / K),
                     "algorithmic_flop_per_launch": flop, "note": note,
                     "hbm": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peaks["hbm_src"]},
-                    "traffic": t, "traffic_over_algorithmic": (t / bytes_alg if t else None)}
+                    "traffic": t, "traffic_over_algorithmic": (t / bytes_alg if (t and bytes_alg) else None),
+                    "dram_gbs_at_traffic": (t / (ms_launch * 1e-3) / 1e9 if (t and ms_launch > 0) else None),
+                    "dram_frac_of_peak_at_traffic": (t / (ms_launch * 1e-3) / 1e9 / peaks["hbm_gbs"] if (t and ms_launch > 0) else None)}
         kernels = [
             entry("k_jac_project", jac_ms, W_PROJ_FLOP * n_local, OBS_BYTES * n_local,
                   "37 pinhole projections per marker observation (residual + quantised central-difference numerators); the reference's a*b+c are two IEEE operations "
