@@ -46,6 +46,7 @@ struct Nccl {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
@@ -56,6 +57,7 @@ struct Nccl {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_err("NCCL: missing symbols"); return false; }
@@ -129,6 +131,8 @@ struct aar_problem {
     cudaGraph_t lm_graph = nullptr; cudaGraphExec_t lm_exec = nullptr; cudaGraphConditionalHandle lm_outer = 0, lm_inner = 0; cudaStream_t lm_side = nullptr;
     bool lm_graph_tried = false, lm_graph_ok = false, capturing = false; long long lm_graph_launches = 0, lm_graph_iters = 0; int lm_body_launches = 0, lm_try_launches = 0;
     DevBuf<LmTraceDev> d_trace;
+    // sharded handles: every rank's reduced system and decision scalars mapped through cudaIpc (aar_kernels.cuh: PeerDev)
+    PeerDev pd; bool peer_ok = false; DevBuf<double> d_peer_small, d_Br_sum; DevBuf<int> d_peer_flags; std::vector<void *> ipc_opened;
     cudaEvent_t ev[16] = {}; double phase_ms[AAR_NUM_PHASES] = {};
 };
 
@@ -359,11 +363,11 @@ int schur_eliminate(aar_problem *p, double *S, double *b) {
 int build_and_solve_reduced(aar_problem *p) {
     const int n_r = p->n_r;
     double *S = p->d_red.p, *b = S + (size_t)n_r * n_r;     // [S | b | Br]: Br = -gr is kept for the gain denominator
+    if (p->peer_ok) LAUNCH(p, k_peer_begin_try, 1, 1, 0, p->pd);      // nobody reads this rank's S of the previous try any more
     if (n_r > 0) LAUNCH(p, k_prepare_reduced, cdiv((long long)n_r * n_r + n_r, 256), 256, 0, n_r, p->d_Hrr.p, p->d_gr.p, S);
     { int rc = schur_eliminate(p, S, b); if (rc) return rc; }
     if (n_r > 0) {
-        int rc = allreduce(p, S, (size_t)n_r * n_r + 2 * n_r, ncclSum);
-        if (rc) return rc;
+        if (!p->peer_ok) { int rc = allreduce(p, S, (size_t)n_r * n_r + 2 * n_r, ncclSum); if (rc) return rc; }
         const int nblk = (n_r + CH_NB - 1) / CH_NB;
         bool done = false;
         if (nblk <= 16 && p->use_cluster_solve) {
@@ -373,7 +377,7 @@ int build_and_solve_reduced(aar_problem *p) {
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             const double *bc = b; const LmState *stp = p->d_st.p;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduced_solve_cluster2, n_r, S, bc, p->d_dr.p, stp, p->d_flag.p, p->d_xinv.p);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduced_solve_cluster2, n_r, S, bc, p->d_dr.p, stp, p->d_flag.p, p->d_xinv.p, p->pd);
             if (e == cudaSuccess) { done = true; p->launches++; }
             else { cudaGetLastError(); p->use_cluster_solve = false; }      // e.g. the cluster cannot be scheduled: fall back for good
         }
@@ -698,6 +702,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     dp.opt_c = p->opt_c; dp.opt_m = p->opt_m; dp.opt_f = p->opt_f; dp.huber = p->huber;
     dp.nrc = p->nrc; dp.nrm = p->nrm; dp.n_r = p->n_r; dp.col_frame0 = p->n_r + 6 * p->f_begin;
     dp.opt_i = p->opt_i; dp.nri = p->nri; dp.col_intr0 = 6 * (p->nrc + p->nrm); dp.st_dev = nullptr;
+    std::memset(&p->pd, 0, sizeof p->pd); p->pd.world = 1;
     dp.h = (double)(p->marker_size / 2.f); // aruco::Marker::get3DPoints: half size in float (marker.cpp:358-369)
     dp.J_delta = p->J_delta;
     dp.obs_f = p->d_obs_f.p; dp.obs_cm = p->d_obs_cm.p; dp.obs_slot_c = p->d_slot_c.p; dp.obs_slot_m = p->d_slot_m.p;
@@ -769,6 +774,7 @@ void aar_problem_destroy(aar_problem *p) {
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_red3) cudaFreeHost(p->h_red3);
     if (p->h_flags) cudaFreeHost(p->h_flags);
+    for (void *q : p->ipc_opened) cudaIpcCloseMemHandle(q);
     if (p->lm_exec) cudaGraphExecDestroy(p->lm_exec);
     if (p->lm_graph) cudaGraphDestroy(p->lm_graph);
     if (p->lm_side) cudaStreamDestroy(p->lm_side);
@@ -1059,7 +1065,7 @@ static bool lm_graph_build(aar_problem *p) {
     p->capturing = true; p->dp.st_dev = p->d_st.p;
     GR(cudaStreamBeginCaptureToGraph(main_stream, body_outer, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)); cap_outer = true;
     if (jacobian_accumulate(p, 0.f, nullptr)) { ok = false; goto done; }
-    k_lm_begin_iter_g<<<1, 1, 0, main_stream>>>(p->d_st.p, p->d_flag.p, p->lm_inner); p->launches++;
+    k_lm_begin_iter_g<<<1, 1, 0, main_stream>>>(p->d_st.p, p->d_flag.p, p->lm_inner, p->comm ? 1 : 0); p->launches++;
     // the inner WHILE node goes in by hand, behind everything captured so far; the capture continues behind it
     GR(cudaStreamGetCaptureInfo_v2(main_stream, &cs, nullptr, &cg, &deps, &ndeps));
     std::memset(&ni, 0, sizeof ni);
@@ -1079,7 +1085,7 @@ static bool lm_graph_build(aar_problem *p) {
         p->launches++;
     }
     residual(p, p->d_zt.p, 0.f, nullptr);
-    k_lm_decide_g<<<1, 1, 0, p->stream>>>(p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->lm_inner); p->launches++;
+    k_lm_decide_g<<<1, 1, 0, p->stream>>>(p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->lm_inner, p->d_flag.p, p->pd); p->launches++;
     k_lm_commit<<<std::max(1, std::min(2 * p->num_sms, (int)cdiv(p->n_vars, 256))), 256, 0, p->stream>>>(p->d_st.p, p->n_vars, p->d_zt.p, p->d_z.p); p->launches++;
     GR(cudaStreamEndCapture(p->lm_side, &tmp)); cap_inner = false;
     p->stream = main_stream;
@@ -1140,7 +1146,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
     if (rep) { rep->trace_len = 0; rep->initial_cost = p->initial_cost; }
     double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
     const char *no_graph = getenv("AAR_NO_GRAPH");           // development aid: host-driven loop only
-    const bool graph_eligible = !p->comm && !p->profiling && !P.verbose && !p->legacy_acc && !p->force_exact_staging && !(no_graph && *no_graph == '1') && p->dp.N > 0;
+    const bool graph_eligible = (!p->comm || p->peer_ok) && !p->profiling && !P.verbose && !p->legacy_acc && !p->force_exact_staging && !(no_graph && *no_graph == '1') && p->dp.N > 0;
     for (int it = 0; it < max_iters && !mustExit; it++) {
         if (graph_eligible && p->h_st->mu >= 0 && (p->lm_graph_ok || !p->lm_graph_tried)) {
             // every iteration but the first of a solve: inside the graph, without the host (see lm_graph_build)
@@ -1150,6 +1156,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
                 const int want = std::min(max_iters - it, LM_TRACE_DEV_CAP);
                 if ((rc = lm_graph_run(p, want, rep, &gd, &gx))) { p->lm_active = false; return rc; }
                 done_iters += gd;
+                if (p->h_flags[3]) { set_err("a peer rank did not answer within the time-out of the peer-memory reduction"); p->lm_active = false; return AAR_ERR_COMM; }
                 if (gx == -1) {
                     int flags[4];
                     CU(cudaMemcpy(flags, p->d_flag.p, sizeof flags, cudaMemcpyDeviceToHost));
@@ -1200,8 +1207,8 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             prof_mark(p, 4);
             residual(p, p->d_zt.p, p->huber_cur, nullptr);
             prof_mark(p, 5);
-            if ((rc = allreduce(p, p->d_red3.p, 3, ncclSum))) return rc;
-            LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->d_flag.p);
+            if (!p->peer_ok && (rc = allreduce(p, p->d_red3.p, 3, ncclSum))) return rc;
+            LAUNCH(p, k_lm_decide, 1, 1, 0, p->d_st.p, p->d_red3.p, n_r, p->d_dr.p, Br, p->d_flag.p, p->pd);
             // an accepted trial point becomes the iterate by a device copy (a pointer swap would invalidate the captured graph of the resident loop)
             LAUNCH(p, k_lm_commit, std::max(1, std::min(2 * p->num_sms, (int)cdiv(p->n_vars, 256))), 256, 0, p->d_st.p, p->n_vars, p->d_zt.p, p->d_z.p);
             if ((rc = fetch_state(p))) return rc;
@@ -1236,6 +1243,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
             it--; continue;
         }
         const int *flags = p->h_flags;                    // fetched with the state of the last try
+        if (flags[3]) { set_err("a peer rank did not answer within the time-out of the peer-memory reduction"); p->lm_active = false; return AAR_ERR_COMM; }
         if (!std::isfinite(p->h_st->trial_cost)) { set_err("non-finite cost at iteration %d", p->iter); p->lm_active = false; return AAR_ERR_NUMERIC; }
         if (flags[0] || flags[2]) {
             // flags[0]: a non-positive pivot in a frame block or in the reduced system (the kernels substituted 1 to keep going):
@@ -1387,13 +1395,66 @@ int aar_comm_init(aar_problem *p, const void *id128) {
     ncclUniqueId id; std::memcpy(&id, id128, sizeof id);
     ncclResult_t r = g_nccl.CommInitRank(&p->comm, p->world, id, p->rank);
     if (r != ncclSuccess) { set_err("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); p->comm = nullptr; return AAR_ERR_COMM; }
+    // ---- peer-memory reduction of the LM try (aar_kernels.cuh: PeerDev): map every rank's reduced system, decision scalars and flag arrays
+    // through cudaIpc; the handles travel by one ncclAllGather.  Any failure, on any rank, keeps the NCCL all-reduces for all of them.
+    {
+        const char *e = getenv("AAR_NO_PEER");
+        int want = (p->world <= PEER_MAX && p->n_r > 0 && p->use_cluster_solve && g_nccl.AllGather && !(e && *e == '1')) ? 1 : 0;
+        struct Handles { cudaIpcMemHandle_t red, small, flags; };
+        Handles mine; std::memset(&mine, 0, sizeof mine);
+        if (want) {
+            if (p->d_peer_small.alloc(8) != cudaSuccess || p->d_peer_flags.alloc(4 * PEER_MAX) != cudaSuccess || p->d_Br_sum.alloc((size_t)p->n_r) != cudaSuccess) want = 0;
+            else {
+                CU(cudaMemsetAsync(p->d_peer_small.p, 0, 8 * sizeof(double), p->stream)); CU(cudaMemsetAsync(p->d_peer_flags.p, 0, 4 * PEER_MAX * sizeof(int), p->stream));
+                if (cudaIpcGetMemHandle(&mine.red, p->d_red.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.small, p->d_peer_small.p) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.flags, p->d_peer_flags.p) != cudaSuccess) { cudaGetLastError(); want = 0; }
+            }
+        }
+        DevBuf<unsigned char> d_send, d_recv; DevBuf<double> d_ok;
+        CU(d_send.alloc(sizeof(Handles))); CU(d_recv.alloc(sizeof(Handles) * (size_t)p->world)); CU(d_ok.alloc(1));
+        CU(cudaMemcpyAsync(d_send.p, &mine, sizeof mine, cudaMemcpyHostToDevice, p->stream));
+        std::vector<Handles> all((size_t)p->world);
+        if (g_nccl.AllGather) {
+            r = g_nccl.AllGather(d_send.p, d_recv.p, sizeof(Handles), ncclChar, p->comm, p->stream);
+            if (r != ncclSuccess) { set_err("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return AAR_ERR_COMM; }
+            CU(cudaMemcpyAsync(all.data(), d_recv.p, sizeof(Handles) * (size_t)p->world, cudaMemcpyDeviceToHost, p->stream));
+            CU(cudaStreamSynchronize(p->stream));
+        }
+        PeerDev pd; std::memset(&pd, 0, sizeof pd);
+        pd.world = p->world; pd.rank = p->rank;
+        if (want) {
+            for (int j = 0; j < p->world && want; j++) {
+                void *q_red = p->d_red.p, *q_small = p->d_peer_small.p, *q_flags = p->d_peer_flags.p;
+                if (j != p->rank) {
+                    if (cudaIpcOpenMemHandle(&q_red, all[(size_t)j].red, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); want = 0; break; }
+                    p->ipc_opened.push_back(q_red);
+                    if (cudaIpcOpenMemHandle(&q_small, all[(size_t)j].small, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); want = 0; break; }
+                    p->ipc_opened.push_back(q_small);
+                    if (cudaIpcOpenMemHandle(&q_flags, all[(size_t)j].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); want = 0; break; }
+                    p->ipc_opened.push_back(q_flags);
+                }
+                pd.red[j] = (const double *)q_red; pd.small[j] = (double *)q_small;
+                pd.flagA[j] = (int *)q_flags; pd.flagB[j] = (int *)q_flags + PEER_MAX; pd.flagC[j] = (int *)q_flags + 2 * PEER_MAX;
+            }
+            pd.epoch = p->d_peer_flags.p + 3 * PEER_MAX; pd.Br_sum = p->d_Br_sum.p; pd.err = p->d_flag.p + 3;
+        }
+        // all ranks or none
+        double okv = want ? 1.0 : 0.0;
+        CU(cudaMemcpyAsync(d_ok.p, &okv, sizeof okv, cudaMemcpyHostToDevice, p->stream));
+        r = g_nccl.AllReduce(d_ok.p, d_ok.p, 1, ncclFloat64, ncclMin, p->comm, p->stream);
+        if (r != ncclSuccess) { set_err("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return AAR_ERR_COMM; }
+        CU(cudaMemcpyAsync(&okv, d_ok.p, sizeof okv, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        p->peer_ok = okv > 0.5;
+        if (p->peer_ok) p->pd = pd; else { p->pd.world = 1; p->pd.rank = 0; }
+    }
     return AAR_OK;
 }
 
 int64_t aar_kernel_launches(const aar_problem *p) { return p ? p->launches : 0; }
 int aar_problem_stats(const aar_problem *p, int64_t *out) {
     if (!p || !out) return AAR_ERR_INVALID;
-    out[0] = p->nslots; out[1] = p->npairs; out[2] = p->nmruns; out[3] = p->schur_fma; out[4] = 0; out[5] = p->max_slots; out[6] = p->f_begin; out[7] = p->f_end;
+    out[0] = p->nslots; out[1] = p->npairs; out[2] = p->nmruns; out[3] = p->schur_fma; out[4] = (p->peer_ok ? 1 : 0) | (p->lm_graph_ok ? 2 : 0) | ((long long)p->lm_graph_iters << 8); out[5] = p->max_slots; out[6] = p->f_begin; out[7] = p->f_end;
     return AAR_OK;
 }
 int aar_set_profiling(aar_problem *p, int32_t on) { if (!p) return AAR_ERR_INVALID; p->profiling = on != 0; for (double &m : p->phase_ms) m = 0; p->track_ms = 0; p->track_runs = 0; return AAR_OK; }

@@ -294,7 +294,9 @@ class Problem:
     def stats(self):
         v = (C.c_int64 * 8)()
         _chk(lib().aar_problem_stats(self.h, v), "aar_problem_stats")
-        return dict(zip(["slots", "pairs", "mruns", "schur_fma", "asm_jobs", "max_slots_per_frame", "frame_begin", "frame_end"], [int(x) for x in v]))
+        d = dict(zip(["slots", "pairs", "mruns", "schur_fma", "mode_bits", "max_slots_per_frame", "frame_begin", "frame_end"], [int(x) for x in v]))
+        d["peer_reduction"] = bool(d["mode_bits"] & 1); d["graph_loop"] = bool(d["mode_bits"] & 2); d["graph_iterations"] = d["mode_bits"] >> 8
+        return d
 
     def set_profiling(self, on=True):
         _chk(lib().aar_set_profiling(self.h, C.c_int32(int(on))), "aar_set_profiling")

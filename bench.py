@@ -496,6 +496,9 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "cameras": rig.C, "markers": rig.M, "frames": rig.F, "marker_observations": n_obs,
                        "corner_observations": int(corner), "num_vars": n_vars, "reduced_system": p.n_r, "parallelism": f"frame-shard x{world}",
+                       "lm_loop": ("graph-resident (%d of the timed + warm-up iterations inside the CUDA graph)" % st["graph_iterations"]) if st["graph_loop"] else "host-driven",
+                       "collective": ("reduced system and decision scalars summed by their consumers over NVLink peer memory (cudaIpc); NCCL for set-up only" if st["peer_reduction"]
+                                      else ("ncclAllReduce per LM try" if world > 1 else "none")),
                        "l2": ("per-step working set %.0f MB per rank (observations + staged Jacobian block, streamed once per step) %s the 126 MB L2; no explicit flush"
                               % ((OBS_BYTES + 2 * STAGE_BYTES) * n_local / 1e6, "exceeds" if (OBS_BYTES + 2 * STAGE_BYTES) * n_local > 2 * 126e6 else "does NOT exceed")),
                        "restart_every": RESTART, "step": "one SparseLevMarq::step (J + JtJ + Schur + solve + trial residual)"},

@@ -32,8 +32,8 @@ enum {
     AAR_OK = 0,
     AAR_ERR_INVALID = 1,      /* bad argument / inconsistent description */
     AAR_ERR_CUDA = 2,         /* CUDA runtime error (no device, launch failure, out of memory) */
-    AAR_ERR_UNSUPPORTED = 3,  /* e.g. optimize_cam_intrinsics, non-pinhole camera matrix */
-    AAR_ERR_COMM = 4,         /* NCCL error */
+    AAR_ERR_UNSUPPORTED = 3,  /* e.g. a non-pinhole camera matrix, more than 4095 cameras */
+    AAR_ERR_COMM = 4,         /* NCCL error, or a peer rank that stopped answering the peer-memory reduction */
     AAR_ERR_NUMERIC = 5       /* non-finite cost or non-positive Cholesky pivot */
 };
 
@@ -127,7 +127,8 @@ int aar_eval_residual(aar_problem *p, const double *z, float huber_delta, double
 int aar_eval_jacobian(aar_problem *p, const double *z, int64_t *colptr, int32_t *rowidx, double *vals);
 /* frame-eliminated normal equations of this rank's shard at z for damping mu (parity hook of the
  * Schur stage): S [n_r*n_r] row-major, UPPER block triangle valid, WITHOUT mu on its diagonal;
- * b [n_r]; cost = sum of squared residuals of the shard. */
+ * b [n_r]; cost = sum of squared residuals of the shard.  n_r = 6 (cameras - 1) + 6 (markers - 1) of the optimised groups; with
+ * optimize_cam_intrinsics 12 more per camera, in the internal order [fx cx fy cy k1 k2 | p1 p2 k3 . . .] (csrc/aar_intrinsics.cuh). */
 int aar_reduced_system(aar_problem *p, const double *z, double mu, double *S, double *b, double *cost);
 
 /* MultiCamMapper::solve() = SparseLevMarq::solve(z, f, J) (multicam_mapper.cpp:419-428,
@@ -162,7 +163,9 @@ int aar_shard_plan(const aar_problem_desc *desc, int32_t *frame_begin, int32_t *
 int aar_row_map(const aar_problem_desc *desc, int64_t capacity, int32_t *obs_frame_idx, int32_t *obs_cam_idx, int32_t *obs_marker_idx,
                 int32_t *obs_has_jacobian, int64_t *num_observations);
 
-/* multi-GPU: one handle per rank; id is the 128-byte ncclUniqueId created on rank 0 */
+/* multi-GPU (one process per GPU of one box): one handle per rank; id is the 128-byte ncclUniqueId created on rank 0.  aar_comm_init
+ * also maps every rank's reduced system through cudaIpc: inside an LM try the all-reduce is fused into its consumers (the reduced
+ * Cholesky sums all ranks' pieces over NVLink peer memory while loading them), NCCL is left with set-up, mu0 and the final gather. */
 int aar_comm_unique_id(void *id128);
 int aar_comm_init(aar_problem *p, const void *id128);
 
@@ -175,7 +178,7 @@ int aar_comm_init(aar_problem *p, const void *id128);
 #define AAR_NUM_PHASES 12
 int64_t aar_kernel_launches(const aar_problem *p);
 /* sizes of this rank's shard: [0] W slots  [1] (frame, camera) pairs  [2] (frame, marker) runs  [3] fused multiply-adds of the upper
- * triangle of the Schur update S -= E E^T per try  [4] assembly jobs  [5] most blocks seen by one frame  [6] [7] frame index range */
+ * triangle of the Schur update S -= E E^T per try  [4] bit 0: peer-memory reduction active (sharded handles), bit 1: graph-resident loop built, bits 8..: LM iterations run inside the graph  [5] most blocks seen by one frame  [6] [7] frame index range */
 int aar_problem_stats(const aar_problem *p, int64_t *out /* [8] */);
 int aar_set_profiling(aar_problem *p, int32_t on);
 int aar_get_phase_ms(const aar_problem *p, double *ms /* [AAR_NUM_PHASES] */);
