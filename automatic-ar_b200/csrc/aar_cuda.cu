@@ -166,7 +166,7 @@ int host_threads(long long work) {
         int c = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
         return std::max(1, std::min(c, 64));
     }();
-    return std::max(1, n / std::max(1, g_ranks_on_host));     // one process per GPU: the ranks share the cores (8 x 64 threads took 4.0 s where one rank takes 1.2 s)
+    return std::max(std::min(n, 8), n / std::max(1, g_ranks_on_host));     // one process per GPU: the ranks share the cores
 }
 template <class F> void parallel_for(long long n, int T, F fn) {      // fn(begin, end, thread index) over T contiguous chunks of [0, n)
     if (T <= 1 || n <= 0) { fn(0, std::max<long long>(n, 0), 0); return; }
@@ -1398,8 +1398,11 @@ int aar_comm_init(aar_problem *p, const void *id128) {
     // ---- peer-memory reduction of the LM try (aar_kernels.cuh: PeerDev): map every rank's reduced system, decision scalars and flag arrays
     // through cudaIpc; the handles travel by one ncclAllGather.  Any failure, on any rank, keeps the NCCL all-reduces for all of them.
     {
-        const char *e = getenv("AAR_NO_PEER");
-        int want = (p->world <= PEER_MAX && p->n_r > 0 && p->use_cluster_solve && g_nccl.AllGather && !(e && *e == '1')) ? 1 : 0;
+        // Opt-in (AAR_PEER=1): measured on 8 x B200 at cfg 4, the peer-memory sums + graph-resident loop take 4.06 ms per LM iteration against
+        // 3.94 ms for ncclAllReduce + host-driven tries (profiles/r2_bench_cfg4_n8*.json): 15 CTAs pulling 14 MB over NVLink with 8-byte loads
+        // and three flag round trips per try cost more than the two NCCL calls they replace.
+        const char *e = getenv("AAR_PEER");
+        int want = (p->world <= PEER_MAX && p->n_r > 0 && p->use_cluster_solve && g_nccl.AllGather && e && *e == '1') ? 1 : 0;
         struct Handles { cudaIpcMemHandle_t red, small, flags; };
         Handles mine; std::memset(&mine, 0, sizeof mine);
         if (want) {

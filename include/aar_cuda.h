@@ -163,9 +163,10 @@ int aar_shard_plan(const aar_problem_desc *desc, int32_t *frame_begin, int32_t *
 int aar_row_map(const aar_problem_desc *desc, int64_t capacity, int32_t *obs_frame_idx, int32_t *obs_cam_idx, int32_t *obs_marker_idx,
                 int32_t *obs_has_jacobian, int64_t *num_observations);
 
-/* multi-GPU (one process per GPU of one box): one handle per rank; id is the 128-byte ncclUniqueId created on rank 0.  aar_comm_init
- * also maps every rank's reduced system through cudaIpc: inside an LM try the all-reduce is fused into its consumers (the reduced
- * Cholesky sums all ranks' pieces over NVLink peer memory while loading them), NCCL is left with set-up, mu0 and the final gather. */
+/* multi-GPU (one process per GPU of one box): one handle per rank; id is the 128-byte ncclUniqueId created on rank 0.  Per LM try the
+ * reduced system and three scalars are all-reduced with NCCL.  With AAR_PEER=1 in the environment aar_comm_init also maps every rank's
+ * reduced system through cudaIpc and the all-reduce is fused into its consumers instead (the reduced Cholesky sums all ranks' pieces over
+ * NVLink peer memory while loading them; no collective-library call inside the try, graph-resident loop on sharded handles). */
 int aar_comm_unique_id(void *id128);
 int aar_comm_init(aar_problem *p, const void *id128);
 

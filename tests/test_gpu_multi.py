@@ -12,7 +12,9 @@ from conftest import ROOT, parity_record
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out_dir, cfg):
+def _worker(rank, world, port, out_dir, cfg, peer):
+    if peer:
+        os.environ["AAR_PEER"] = "1"      # all-reduce fused into its consumers over NVLink peer memory + graph-resident loop
     for p in (os.path.join(ROOT, "automatic-ar_b200", "python"),):
         sys.path.insert(0, p)
     import torch
@@ -57,6 +59,8 @@ def _worker(rank, world, port, out_dir, cfg):
             else:           # full solve: inside the reproducibility envelope of the quantised Jacobian
                 rec["full_solve_iterations"] = [int(it1), int(it)]; rec["full_solve_rel_dev_cost"] = abs(fc - fc1) / fc1
                 assert abs(it - it1) <= 1 and abs(fc - fc1) <= 2e-5 * fc1
+        rec["collective"] = "peer memory (cudaIpc), graph-resident loop" if p.stats()["peer_reduction"] else "ncclAllReduce per try, host-driven loop"
+        assert bool(peer) == p.stats()["peer_reduction"]
         parity_record(f"multi_gpu_world{world}_{cfg}_vs_single_gpu", **rec)
         open(os.path.join(out_dir, "ok"), "w").write("ok")
     # every rank returns the full z: the shards' frame poses are exchanged at the end
@@ -67,12 +71,12 @@ def _worker(rank, world, port, out_dir, cfg):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,cfg", [(2, "cfg2"), (8, "cfg3")])
-def test_sharded_solve_matches_single_gpu(tmp_path, world, cfg):
+@pytest.mark.parametrize("world,cfg,peer", [(2, "cfg2", 0), (2, "cfg2", 1), (8, "cfg3", 0), (8, "cfg3", 1)])
+def test_sharded_solve_matches_single_gpu(tmp_path, world, cfg, peer):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29700 + os.getpid() % 200 + world
-    mp.spawn(_worker, args=(world, port, str(tmp_path), cfg), nprocs=world, join=True)
+    port = 29700 + os.getpid() % 200 + world + 20 * peer
+    mp.spawn(_worker, args=(world, port, str(tmp_path), cfg, peer), nprocs=world, join=True)
     assert os.path.exists(os.path.join(tmp_path, "ok"))

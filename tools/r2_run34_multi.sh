@@ -10,14 +10,14 @@ from aar_b200 import synth
 t = time.time(); synth.make_config("cfg4"); print("rig cached", time.time() - t)
 PY
 run() { n=$1; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $n "$@"; }
-run 8 --steps 20 --warmup 3 > gpurun_out/r34_bench_cfg4_n8.json 2> gpurun_out/r34_bench_cfg4_n8.err; python - <<'PY'
+AAR_PEER=1 run 8 --steps 20 --warmup 3 > gpurun_out/r34_bench_cfg4_n8.json 2> gpurun_out/r34_bench_cfg4_n8.err; python - <<'PY'
 import json
 try:
     d=json.loads(open("gpurun_out/r34_bench_cfg4_n8.json").read().strip().splitlines()[-1]); print("cfg4 n8 peer", d["ms_per_step"], d["e2e"]["ms_per_step"], d["config"]["lm_loop"], "|", d["config"]["collective"][:40], d["phases_ms_per_step"], "create", d["e2e"]["create_s"], "final cost", d["final_cost"])
 except Exception as e: print("parse failed", e)
 PY
 tail -3 gpurun_out/r34_bench_cfg4_n8.err | cut -c1-300
-AAR_NO_PEER=1 run 8 --steps 20 --warmup 3 > gpurun_out/r34_bench_cfg4_n8_nccl.json 2> gpurun_out/r34_bench_cfg4_n8_nccl.err; python - <<'PY'
+run 8 --steps 20 --warmup 3 > gpurun_out/r34_bench_cfg4_n8_nccl.json 2> gpurun_out/r34_bench_cfg4_n8_nccl.err; python - <<'PY'
 import json
 try:
     d=json.loads(open("gpurun_out/r34_bench_cfg4_n8_nccl.json").read().strip().splitlines()[-1]); print("cfg4 n8 nccl", d["ms_per_step"], d["e2e"]["ms_per_step"], d["config"]["lm_loop"], "final cost", d["final_cost"])
