@@ -13,6 +13,7 @@
 #include <queue>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -205,12 +206,21 @@ int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) 
     const int K = cams ? h->num_cams : (int)h->marker_list.size();
     if ((long long)K * K > (1LL << 26)) { ierr("too many %s (%d) for the pair tables of the rig initialisation", cams ? "cameras" : "markers", K); return AAR_ERR_UNSUPPORTED; }
     auto rank_of_member = [&](int id) { return cams ? id : (int)(std::lower_bound(h->marker_list.begin(), h->marker_list.end(), id) - h->marker_list.begin()); };
-    std::vector<long long> count((size_t)K * K, 0), seen((size_t)K * K, 0);
-    std::vector<std::vector<int2>> lists((size_t)K * K);
+    // Two passes over the frames, both threaded over contiguous frame ranges: pass 0 counts the candidates of every (id1, id2) per
+    // thread; the prefix sums over the threads give every thread the list position its range starts at, so that pass 1 can decide
+    // which candidates survive `consensus_max` and collect them independently; concatenating the threads' lists in order gives the
+    // list of the sequential scan (25.6 M detections: 8.0 s single-threaded).
+    const size_t KK = (size_t)K * K;
+    int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16, ((size_t)1 << 24) / std::max<size_t>(KK, 1), (size_t)std::max(1, h->num_frames / 64)}));
+    std::vector<std::vector<long long>> count_t((size_t)T, std::vector<long long>(KK, 0));
+    std::vector<std::vector<std::vector<int2>>> lists_t((size_t)T, std::vector<std::vector<int2>>(KK));
+    std::vector<long long> count(KK, 0);
     struct Mem { int group, member_rank; long long det; };
-    std::vector<Mem> members;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int f = 0; f < h->num_frames; f++) {
+    auto scan = [&](int t, int pass) {
+        const int f0 = (int)((long long)h->num_frames * t / T), f1 = (int)((long long)h->num_frames * (t + 1) / T);
+        std::vector<long long> &cnt = count_t[(size_t)t];      // pass 0: counts of this range; pass 1: running list positions (start = prefix over the threads)
+        std::vector<Mem> members;
+        for (int f = f0; f < f1; f++) {
             if (!h->frame_kept[f]) continue;
             members.clear();
             for (long long d = h->frame_first[f]; d < h->frame_first[f + 1]; d++)
@@ -230,13 +240,13 @@ int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) 
                                 for (size_t b = a1; b < g1; b++) {
                                     const size_t key = row + (size_t)members[b].member_rank;
                                     const int nb = h->ncand[members[b].det];
-                                    if (pass == 0) count[key] += nb;
+                                    if (pass == 0) cnt[key] += nb;
                                     else {
-                                        long long &pos = seen[key];
+                                        long long &pos = cnt[key];
                                         const long long n = count[key];
                                         for (int j = 0; j < nb; j++, pos++)
                                             if (kept_position(pos, n, h->consensus_max))
-                                                lists[key].push_back(make_int2((int)(2 * members[a].det + i), (int)(2 * members[b].det + j)));
+                                                lists_t[(size_t)t][key].push_back(make_int2((int)(2 * members[a].det + i), (int)(2 * members[b].det + j)));
                                     }
                                 }
                         a0 = a1;
@@ -244,8 +254,24 @@ int rig_consensus(aar_init *h, bool cams, Best &best, std::vector<Edge> &edges) 
                 g0 = g1;
             }
         }
-        if (pass == 0 && h->consensus_max > 0) for (size_t k = 0; k < lists.size(); k++) if (count[k]) lists[k].reserve((size_t)std::min<long long>(count[k], h->consensus_max));
+    };
+    auto run_pass = [&](int pass) {
+        if (T == 1) { scan(0, pass); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(scan, t, pass);
+        for (auto &x : th) x.join();
+    };
+    run_pass(0);
+    for (size_t k = 0; k < KK; k++) { long long run = 0; for (int t = 0; t < T; t++) { const long long c = count_t[(size_t)t][k]; count_t[(size_t)t][k] = run; run += c; } count[k] = run; }
+    run_pass(1);
+    std::vector<std::vector<int2>> lists(KK);
+    for (size_t k = 0; k < KK; k++) {
+        if (!count[k]) continue;
+        size_t n = 0; for (int t = 0; t < T; t++) n += lists_t[(size_t)t][k].size();
+        lists[k].reserve(n);
+        for (int t = 0; t < T; t++) lists[k].insert(lists[k].end(), lists_t[(size_t)t][k].begin(), lists_t[(size_t)t][k].end());
     }
+    { std::vector<std::vector<std::vector<int2>>>().swap(lists_t); }
     std::vector<int2> src; std::vector<long long> seg_begin(1, 0), seg_count; std::vector<Key> keys;
     for (int r1 = 0; r1 < K; r1++)                              // (id1, id2) ascending: the iteration order of the reference's nested maps
         for (int r2 = 0; r2 < K; r2++) {
@@ -421,19 +447,33 @@ int aar_init_object_transforms(aar_init *h) {
     ICU(cudaSetDevice(h->device));
     h->object_T.clear();
     // candidate list of a frame: markers ascending, cameras ascending, detection order, candidates (initializer.cpp:76-110)
+    // threaded over contiguous frame ranges; the threads' pieces are concatenated in order
+    const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16, (size_t)std::max(1, h->num_frames / 256)}));
+    std::vector<std::vector<int>> src_t((size_t)T), len_t((size_t)T), frame_t((size_t)T);
+    auto scan = [&](int t) {
+        const int f0 = (int)((long long)h->num_frames * t / T), f1 = (int)((long long)h->num_frames * (t + 1) / T);
+        std::vector<std::pair<std::pair<int, int>, long long>> members;
+        std::vector<int> one;
+        for (int f = f0; f < f1; f++) {
+            if (!h->frame_kept[f]) continue;
+            members.clear();
+            for (long long d = h->frame_first[f]; d < h->frame_first[f + 1]; d++) if (h->ncand[d]) members.push_back({{h->det_marker[d], h->det_cam[d]}, d});
+            std::stable_sort(members.begin(), members.end(), [](const std::pair<std::pair<int, int>, long long> &a, const std::pair<std::pair<int, int>, long long> &b) { return a.first < b.first; });
+            one.clear();
+            for (auto &m : members) for (int k = 0; k < h->ncand[m.second]; k++) one.push_back((int)(2 * m.second + k));
+            const long long n = (long long)one.size();
+            int kept = 0;
+            for (long long pos = 0; pos < n; pos++) if (kept_position(pos, n, h->consensus_max)) { src_t[(size_t)t].push_back(one[pos]); kept++; }
+            len_t[(size_t)t].push_back(kept); frame_t[(size_t)t].push_back(f);
+        }
+    };
+    if (T == 1) scan(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(scan, t); for (auto &x : th) x.join(); }
     std::vector<int> src; std::vector<long long> seg_begin(1, 0); std::vector<int> seg_frame;
-    std::vector<std::pair<std::pair<int, int>, long long>> members;
-    std::vector<int> one;
-    for (int f = 0; f < h->num_frames; f++) {
-        if (!h->frame_kept[f]) continue;
-        members.clear();
-        for (long long d = h->frame_first[f]; d < h->frame_first[f + 1]; d++) if (h->ncand[d]) members.push_back({{h->det_marker[d], h->det_cam[d]}, d});
-        std::stable_sort(members.begin(), members.end(), [](const std::pair<std::pair<int, int>, long long> &a, const std::pair<std::pair<int, int>, long long> &b) { return a.first < b.first; });
-        one.clear();
-        for (auto &m : members) for (int k = 0; k < h->ncand[m.second]; k++) one.push_back((int)(2 * m.second + k));
-        const long long n = (long long)one.size();
-        for (long long pos = 0; pos < n; pos++) if (kept_position(pos, n, h->consensus_max)) src.push_back(one[pos]);
-        seg_begin.push_back((long long)src.size()); seg_frame.push_back(f);
+    { size_t n = 0; for (auto &v : src_t) n += v.size(); src.reserve(n); }
+    for (int t = 0; t < T; t++) {
+        src.insert(src.end(), src_t[(size_t)t].begin(), src_t[(size_t)t].end());
+        for (size_t i = 0; i < len_t[(size_t)t].size(); i++) { seg_begin.push_back(seg_begin.back() + len_t[(size_t)t][i]); seg_frame.push_back(frame_t[(size_t)t][i]); }
     }
     if (src.empty()) return AAR_OK;
     ICU(cudaEventRecord(h->ev0, h->stream));
