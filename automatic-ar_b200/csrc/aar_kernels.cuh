@@ -269,15 +269,19 @@ __global__ void __launch_bounds__(BS_WARPS * 32, AAR_BS_MINBLOCKS) k_backsub(Dev
     for (int f = blockIdx.x * BS_WARPS + warp; f < p.F; f += gridDim.x * BS_WARPS) {
         double acc[6] = {0, 0, 0, 0, 0, 0};
         const int s0 = p.frame_slot_ptr[f], s1 = p.frame_slot_ptr[f + 1];
-        for (int s = s0 + lane; s < s1; s += 32) {
-            const double *w = W + (size_t)s * 36;
-            const double *d = dr + 6 * p.slot_block[s];
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const double di = d[i];
-#pragma unroll
-                for (int k = 0; k < 6; k++) acc[k] = fma(w[i * 6 + k], di, acc[k]);
-            }
+        // the W blocks of a frame are (s1 - s0) * 36 consecutive doubles: lanes walk them as double2 (coalesced 16-byte loads; a lane per
+        // slot left half of every sector unused per instruction).  Pair e2 of the range = slot e2 / 18, row i = (e2 % 18) / 3 of W_s,
+        // columns 2 (e2 % 3) and + 1: acc[k] += W_s[i][k] * delta_r[blk(s)][i]
+        const double2 *w2 = reinterpret_cast<const double2 *>(W + (size_t)s0 * 36);
+        const int npair = (s1 - s0) * 18;
+        for (int e2 = lane; e2 < npair; e2 += 32) {
+            const int sl = e2 / 18, r = e2 - 18 * sl, i = r / 3, c = r - 3 * i;
+            const double2 w = w2[e2];
+            const double di = dr[6 * p.slot_block[s0 + sl] + i];
+            const double m0 = c == 0 ? di : 0.0, m1 = c == 1 ? di : 0.0, m2 = c == 2 ? di : 0.0;
+            acc[0] = fma(w.x, m0, acc[0]); acc[1] = fma(w.y, m0, acc[1]);
+            acc[2] = fma(w.x, m1, acc[2]); acc[3] = fma(w.y, m1, acc[3]);
+            acc[4] = fma(w.x, m2, acc[4]); acc[5] = fma(w.y, m2, acc[5]);
         }
 #pragma unroll
         for (int k = 0; k < 6; k++)
