@@ -296,7 +296,7 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump, bool de
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
     if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, p->d_z.p, p->d_intr.p);
-    if (p->npairs > 0) LAUNCH(p, k_pair_tab, std::max(1, std::min(p->npairs, 16 * p->num_sms)), PAIR_TAB, 0, p->dp);
+    if (p->npairs > 0) LAUNCH(p, k_pair_tab, std::max(1, std::min(p->npairs, 10 * p->num_sms)), PAIR_TAB, 0, p->dp);      // 10 CTAs of 192 threads per SM: one full wave
     if (Jdump) {
         if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump);
         if (p->opt_i && p->dp.N > 0) { if (p->d_Ji.n < 32 * (size_t)p->dp.N) CU(p->d_Ji.alloc(32 * (size_t)p->dp.N)); LAUNCH(p, k_intr_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, p->d_Ji.p); }
