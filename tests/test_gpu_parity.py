@@ -59,6 +59,8 @@ def test_index_maps_bit_exact(binding, oracle_mod):
     assert np.array_equal(v_o, v_g)
     r_g, _ = p.residual(z)
     assert np.array_equal(r_g, o.error(z))
+    parity_record("index_maps_sparsity_pattern_jacobian_residual_with_erasures_and_duplicates", observations=int(p.num_obs), jacobian_nnz=int(len(v_g)),
+                  erased_or_duplicate_detections=4, bit_exact=True)
 
 
 @pytest.mark.parametrize("distorted", [False, True])
@@ -88,6 +90,8 @@ def test_residual_and_jacobian_bit_exact(binding, oracle_mod, distorted):
     flips = (o.error(z0) != p.residual(z0)[0]).sum()
     o.set_sincos_mode(1)
     assert flips <= 2
+    parity_record("undistortion_residual_jacobian_vs_oracle", distorted=bool(distorted), residual_rows=int(len(r_o)), jacobian_nnz=int(len(v_o)), bit_exact=True,
+                  float32_flips_against_libm_sincos_oracle=int(flips))
 
 
 def test_config_flags_and_huber(binding, oracle_mod):
@@ -117,6 +121,8 @@ def test_reduced_system_matches_oracle(binding, oracle_mod):
     assert np.abs(S_g[iu] - S_o[iu]).max() <= 1e-10 * scale        # sums of products in a different order
     assert np.abs(b_g - b_o).max() <= 1e-10 * np.abs(b_o).max()
     assert abs(c_g - c_o) <= 1e-12 * c_o
+    parity_record("reduced_schur_system_vs_oracle", n_r=int(p.n_r), rel_dev_S=float(np.abs(S_g[iu] - S_o[iu]).max() / scale),
+                  rel_dev_b=float(np.abs(b_g - b_o).max() / np.abs(b_o).max()), rel_dev_cost=float(abs(c_g - c_o) / c_o), bar=1e-10)
 
 
 def _oracle_envelope(o, z0, fc_o, z_o, n=3, eps=1e-13):
@@ -256,6 +262,12 @@ def test_full_size_properties_cfg3(binding, oracle_mod):
     assert 0.25 < rms < 0.35                                             # 0.3 px corner noise
     r_fin = o.error(z_g)
     assert abs(r_fin @ r_fin - fc) <= 1e-9 * fc
+    o.set_sincos_mode(0)
+    flips = int((o.error(z0) != r_g).sum())                               # the same residuals against the libm-sincos oracle (what cv::Rodrigues calls)
+    o.set_sincos_mode(1)
+    parity_record("cfg3_full_size_residual_and_solve", observations=int(p.num_obs), residual_rows=int(len(r_o)), residual_bit_exact=True,
+                  float32_flips_against_libm_sincos_oracle=flips, iterations=int(it), rms_px=float(rms), oracle_cost_at_device_z_rel_dev=float(abs(r_fin @ r_fin - fc) / fc))
+    assert flips <= 1e-5 * len(r_o)
 
 
 def _track_against_reference(binding, oracle_mod, rig, with_huber, tol, label, frames=None):
