@@ -3,6 +3,7 @@
 // device-resident Levenberg-Marquardt loop, NCCL all-reduce of the reduced system for frame shards.
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -420,6 +421,9 @@ void aar_lm_default_params(aar_lm_params *q) {
 }
 
 static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_only) {
+    // AAR_CREATE_TIMING=1: wall-clock of the stages of this function to stderr (development aid)
+    const bool ctime = getenv("AAR_CREATE_TIMING") != nullptr; auto ct0 = std::chrono::steady_clock::now();
+    auto cmark = [&](const char *what) { if (!ctime) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "aar_problem_create: %-28s %.3f s\n", what, std::chrono::duration<double>(t - ct0).count()); ct0 = t; };
     if (!d || !out) { set_err("null argument"); return AAR_ERR_INVALID; }
     *out = nullptr;
     if (d->num_cams < 1 || d->num_markers < 1 || d->num_frames < 0 || d->num_cams > 4095 || d->num_markers > 500000) { set_err("bad counts"); return AAR_ERR_INVALID; }
@@ -462,6 +466,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     const long long nd = d->num_detections;
     const IdMap fmap(p->frame_ids), cmap(p->cam_ids), mmap(p->marker_ids);
     std::vector<int> kf((size_t)nd), kc((size_t)nd), km((size_t)nd);
+    cmark("copies, id maps");
     std::vector<long long> keep;
     {
         const int T = host_threads(nd);
@@ -520,6 +525,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     p->o_begin = frame_ptr[(size_t)p->f_begin]; p->o_end = frame_ptr[(size_t)p->f_end];
     const int Fl = p->f_end - p->f_begin; const long long Nl = p->o_end - p->o_begin;
 
+    cmark("row map, shard");
     // ---- W slots: per local frame, the distinct active camera blocks seen (order of first appearance), then the
     // distinct active marker blocks; cs_cum / ms_cum are the running numbers of camera / marker slots.
     // Two passes over the local frames (count, prefix sum, fill), both parallel.
@@ -601,6 +607,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) == cudaSuccess && v > 0) p->smem_optin = (size_t)v;
     }
 
+    cmark("W slots, device set-up");
     std::vector<int> obs_f((size_t)Nl), obs_cm((size_t)Nl);
     std::vector<float4> raw_a((size_t)Nl), raw_b((size_t)Nl);
     parallel_for(Nl, host_threads(Nl), [&](long long b0, long long b1, int) {
@@ -626,6 +633,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     for (int m = 0; m < p->M; m++) pose12_from_T16(&p->marker_T[16 * (size_t)m], &fixed_m[12 * (size_t)m]);
     for (int f = 0; f < Fl; f++) pose12_from_T16(&p->frame_T[16 * (size_t)(p->f_begin + f)], &fixed_f[12 * (size_t)f]);
 
+    cmark("observation arrays, pairs");
 #define UP(buf, vec)                                                                                             \
     do { CU((buf).alloc((vec).size())); if ((vec).size()) CU(cudaMemcpyAsync((buf).p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream)); } while (0)
     UP(p->d_obs_f, obs_f); UP(p->d_obs_cm, obs_cm); UP(p->d_slot_c, slot_c); UP(p->d_slot_m, slot_m);
@@ -697,6 +705,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     CU(cudaMemsetAsync(p->d_flag.p, 0, 4 * sizeof(int), p->stream));
     CU(cudaMemsetAsync(p->d_st.p, 0, sizeof(LmState), p->stream));
 
+    cmark("visiting orders, uploads, allocations");
     DevProblem &dp = p->dp;
     dp.C = p->C; dp.M = p->M; dp.F = Fl; dp.N = Nl; dp.root_cam = p->root_cam; dp.root_marker = p->root_marker;
     dp.opt_c = p->opt_c; dp.opt_m = p->opt_m; dp.opt_f = p->opt_f; dp.huber = p->huber;
@@ -735,6 +744,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     }
     CU(cudaFuncSetAttribute(k_schur_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SP_TILE_BYTES + (size_t)p->n_r * sizeof(double))));
     CU(cudaStreamSynchronize(p->stream));
+    cmark("undistortion, attributes, sync");
     aar_lm_default_params(&p->params);
     guard.release();
     *out = p;
