@@ -39,6 +39,7 @@
 #include <omp.h>
 
 #include "../include/aar_crsincos.h"
+#include "../include/aar_analytic.h"
 
 #ifdef AAR_ORACLE_WITH_REFERENCE_SLM
 #include <Eigen/Sparse>
@@ -90,6 +91,9 @@ struct Triplet { int row, col; double val; };
 
 struct Mcm {
     bool with_huber = false;
+    /* analytic-Jacobian / full-FP64 variant (include/aar_analytic.h): residual in double with no float32
+     * rounding, Jacobian by differentiation instead of central differences.  NOT the reference's arithmetic. */
+    bool analytic = false;
     MatArrays mat_arrays;
     Config config;
     double J_delta = 0.001;
@@ -307,6 +311,83 @@ struct Mcm {
         return std::sqrt(hubberMono(SqErr, delta) / SqErr);
     }
 
+
+    /* ---- analytic variant: the per-observation inputs of aar_an_observation (include/aar_analytic.h) */
+    struct AnObs { double Ri[9], ti[3], dRc[27], tc[3], Ro[9], to[3], dRo[27], Rm[9], tm[3], dRm[27], fx, cx, fy, cy, h; bool act_c, act_m, act_f; long col_c, col_m, col_f; };
+    static void split34(const M4 &T, double *R, double *t) { for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[i * 3 + j] = T.a[i * 4 + j]; t[i] = T.a[i * 4 + 3]; } }
+    /* `input` may be null when only the residual is wanted (no derivative tables, no active blocks) */
+    void an_gather(const MatArrays &ma, const eVec *input, int frame_id, int cam_id, int marker_id, AnObs &q) const {
+        const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        std::memset(&q, 0, sizeof q);
+        size_t off = 0;
+        { /* camera: Xc = inv(Tc) Xo, skipped for the root camera (mcm.cpp:617-621) */
+            const MatArray &src = config.optimize_cam_poses ? ma.transforms_to_root_cam : mat_arrays.transforms_to_root_cam;
+            const size_t idx = (size_t)src.m.at(cam_id), ridx = (size_t)src.m.at((int)root_cam);
+            if ((size_t)cam_id == root_cam) { std::memcpy(q.Ri, I9, sizeof I9); }
+            else { M4 inv = inv44(src.v[idx]); split34(inv, q.Ri, q.ti); }
+            q.act_c = input && config.optimize_cam_poses && (size_t)cam_id != root_cam;
+            q.col_c = (long)(off + 6 * (idx - (idx > ridx ? 1 : 0)));
+            if (q.act_c) { double R[9]; split34(src.v[idx], R, q.tc); aar_an_rodrigues_derivs(&(*input)[(size_t)q.col_c], R, q.dRc); }
+            if (config.optimize_cam_poses) off += (num_cameras - 1) * 6;
+        }
+        { /* marker, skipped for the root marker (mcm.cpp:624-628) */
+            const MatArray &src = config.optimize_marker_poses ? ma.transforms_to_root_marker : mat_arrays.transforms_to_root_marker;
+            const size_t idx = (size_t)src.m.at(marker_id), ridx = (size_t)src.m.at((int)root_marker);
+            if ((size_t)marker_id == root_marker) std::memcpy(q.Rm, I9, sizeof I9); else split34(src.v[idx], q.Rm, q.tm);
+            q.act_m = input && config.optimize_marker_poses && (size_t)marker_id != root_marker;
+            q.col_m = (long)(off + 6 * (idx - (idx > ridx ? 1 : 0)));
+            if (q.act_m) aar_an_rodrigues_derivs(&(*input)[(size_t)q.col_m], q.Rm, q.dRm);
+            if (config.optimize_marker_poses) off += (num_markers - 1) * 6;
+        }
+        { /* frame */
+            const MatArray &src = config.optimize_object_poses ? ma.object_to_global : mat_arrays.object_to_global;
+            const size_t idx = (size_t)src.m.at(frame_id);
+            split34(src.v[idx], q.Ro, q.to);
+            q.act_f = input && config.optimize_object_poses;
+            q.col_f = (long)(off + 6 * idx);
+            if (q.act_f) aar_an_rodrigues_derivs(&(*input)[(size_t)q.col_f], q.Ro, q.dRo);
+        }
+        const M4 &K = mat_arrays.cam_mats.at_id(cam_id);
+        q.fx = K.a[0]; q.cx = K.a[2]; q.fy = K.a[5]; q.cy = K.a[6];
+        q.h = marker_points_3d_mat.a[1]; /* +halfSize, computed in float (marker.cpp:358-369) */
+    }
+    struct AnTripletSink {
+        std::vector<Triplet> *out; size_t row0; long col_c, col_m, col_f;
+        void put(int col, int corner, double jx, double jy) {
+            const int blk = col / 6, d = col % 6;
+            const long c = (blk == 0 ? col_c : blk == 1 ? col_m : col_f) + d;
+            out->push_back({(int)(row0 + 2 * corner), (int)c, jx}); out->push_back({(int)(row0 + 2 * corner + 1), (int)c, jy});
+        }
+    };
+    void an_residual8(const AnObs &q, const Marker &mk, double *e) const {
+        float und[8]; for (int i = 0; i < 4; i++) { und[2 * i] = mk.x[i]; und[2 * i + 1] = mk.y[i]; }
+        aar_an_null_sink ns;
+        aar_an_observation(q.Ri, q.ti, q.dRc, q.tc, q.Ro, q.to, q.dRo, q.Rm, q.tm, q.dRm, q.fx, q.cx, q.fy, q.cy, q.h, und, false, false, false, e, ns);
+    }
+    /* the same projection through the restated OpenCV chain of project_marker (mul44 / inv44, K * T34 * X), kept in double:
+     * written independently of include/aar_analytic.h; tests/test_analytic_cpu.py differentiates THIS numerically */
+    void project_marker_fp64(const MatArrays &ma, size_t frame_id, size_t marker_id, size_t cam_id, double px[4], double py[4]) const {
+        auto pick = [&](const MatArray &opt, const MatArray &fixed, bool optimized, size_t id) -> const M4 & { const MatArray &src = optimized ? opt : fixed; return src.v[(size_t)src.m.at((int)id)]; };
+        M4 transform = pick(ma.object_to_global, mat_arrays.object_to_global, config.optimize_object_poses, frame_id);
+        if (cam_id != root_cam) transform = mul44(inv44(pick(ma.transforms_to_root_cam, mat_arrays.transforms_to_root_cam, config.optimize_cam_poses, cam_id)), transform);
+        if (marker_id != root_marker) transform = mul44(transform, pick(ma.transforms_to_root_marker, mat_arrays.transforms_to_root_marker, config.optimize_marker_poses, marker_id));
+        const M4 &cam_mat = mat_arrays.cam_mats.at_id((int)cam_id);
+        double KT[12], P[12];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) KT[i * 4 + j] = cam_mat.a[i * 4 + 0] * transform.a[0 * 4 + j] + cam_mat.a[i * 4 + 1] * transform.a[1 * 4 + j] + cam_mat.a[i * 4 + 2] * transform.a[2 * 4 + j];
+        const double *X = marker_points_3d_mat.a;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) P[i * 4 + j] = KT[i * 4 + 0] * X[0 * 4 + j] + KT[i * 4 + 1] * X[1 * 4 + j] + KT[i * 4 + 2] * X[2 * 4 + j] + KT[i * 4 + 3] * X[3 * 4 + j];
+        for (int c = 0; c < 4; c++) { px[c] = P[0 * 4 + c] / P[2 * 4 + c]; py[c] = P[1 * 4 + c] / P[2 * 4 + c]; }
+    }
+    void error_function_fp64_chain(const eVec &input, eVec &error) const {
+        MatArrays ma; ma_init(ma); eVec2Mats(input, ma);
+        error.assign(num_point_xys, 0.0);
+        size_t index = 0;
+        for (auto &f : frame_cam_markers) for (auto &c : f.second) for (auto &mk : c.second) {
+            double px[4], py[4]; project_marker_fp64(ma, (size_t)f.first, (size_t)mk.id, (size_t)c.first, px, py);
+            for (int i = 0; i < 4; i++) { error[index++] = (double)mk.x[i] - px[i]; error[index++] = (double)mk.y[i] - py[i]; }
+        }
+    }
+
     /* mcm.cpp:996-1028 */
     void eval_curr_solution(const MatArrays &ma, eVec &error) const {
         error.assign(num_point_xys, 0.0);
@@ -317,11 +398,13 @@ struct Mcm {
                 size_t cam_id = it->first;
                 const std::vector<Marker> &markers = it->second;
                 for (size_t m = 0; m < markers.size(); m++) {
-                    float px[4], py[4];
-                    project_marker(ma, nullptr, frame_id, markers[m].id, cam_id, px, py);
+                    float px[4], py[4]; double e8[8];
+                    if (analytic) { AnObs q; an_gather(ma, nullptr, frame_id, (int)cam_id, markers[m].id, q); an_residual8(q, markers[m], e8); }
+                    else project_marker(ma, nullptr, frame_id, markers[m].id, cam_id, px, py);
                     for (int i = 0; i < 4; i++) {
                         double ex = markers[m].x[i] - px[i]; /* float - float, widened afterwards */
                         double ey = markers[m].y[i] - py[i];
+                        if (analytic) { ex = e8[2 * i]; ey = e8[2 * i + 1]; }
                         if (with_huber) {
                             double e = ex * ex + ey * ey;
                             double w = getHubberMonoWeight(e, hubberDelta);
@@ -436,6 +519,19 @@ struct Mcm {
     void jacobian_triplets(const eVec &input, std::vector<Triplet> &all) const {
         MatArrays ma; ma_init(ma); eVec2Mats(input, ma);
         all.clear();
+        if (analytic) { /* one 8 x 18 block per observation that owns Jacobian rows (the last of a repeated (frame, cam, marker), mcm.cpp:368-370) */
+            size_t row0 = 0;
+            for (auto &f : frame_cam_markers) for (auto &c : f.second) for (auto &mk : c.second) {
+                if (frame_cam_marker.at(f.first).at(c.first).at(mk.id).second == row0) {
+                    AnObs q; an_gather(ma, &input, f.first, c.first, mk.id, q);
+                    float und[8]; for (int i = 0; i < 4; i++) { und[2 * i] = mk.x[i]; und[2 * i + 1] = mk.y[i]; }
+                    double e8[8]; AnTripletSink sink{&all, row0, q.col_c, q.col_m, q.col_f};
+                    aar_an_observation(q.Ri, q.ti, q.dRc, q.tc, q.Ro, q.to, q.dRo, q.Rm, q.tm, q.dRm, q.fx, q.cx, q.fy, q.cy, q.h, und, q.act_c, q.act_m, q.act_f, e8, sink);
+                }
+                row0 += 8;
+            }
+            return;
+        }
         size_t param_offset = 0;
         auto run = [&](param_type t, long long n, std::function<bool(long long)> skip) {
             std::vector<std::vector<Triplet>> elems((size_t)n);
@@ -588,6 +684,15 @@ void aar_oracle_set_config(OracleHandle *h, int cams, int markers, int objects, 
 }
 /* SparseLevMarq::Params::maxIters as MultiCamMapper sets it (mcm.cpp:326-330); tests lower it to compare single LM steps */
 void aar_oracle_set_max_iters(OracleHandle *h, int max_iters) { h->mcm.maxIters = max_iters; }
+/* analytic-Jacobian / full-FP64 variant (include/aar_analytic.h); requires intrinsics off */
+void aar_oracle_set_analytic(OracleHandle *h, int on) { h->mcm.analytic = on != 0; }
+/* m - p of the restated OpenCV chain kept in double (no float32 rounding, no Huber): the function the analytic Jacobian is
+ * differentiated against numerically in tests/test_analytic_cpu.py */
+void aar_oracle_error_fp64_chain(OracleHandle *h, const double *z, double *r) {
+    eVec e(z, z + h->mcm.num_vars), err; h->mcm.error_function_fp64_chain(e, err);
+    std::memcpy(r, err.data(), err.size() * sizeof(double));
+}
+void aar_oracle_rodrigues_derivs(const double *r, double *dR) { double R[9]; rodrigues_vec2mat(r, R); aar_an_rodrigues_derivs(r, R, dR); }
 int64_t aar_oracle_num_vars(OracleHandle *h) { return (int64_t)h->mcm.num_vars; }
 int64_t aar_oracle_num_rows(OracleHandle *h) { return (int64_t)h->mcm.num_point_xys; }
 

@@ -91,6 +91,15 @@ class Oracle:
     def set_max_iters(self, n):
         self.L.aar_oracle_set_max_iters(self.h, C.c_int(int(n)))
 
+    def set_analytic(self, on=True):
+        """analytic-Jacobian / full-FP64 variant (include/aar_analytic.h): error(), jacobian(), reduced_system() and the solves follow it."""
+        self.L.aar_oracle_set_analytic(self.h, C.c_int(int(on)))
+
+    def error_fp64_chain(self, z):
+        """m - p of the restated OpenCV chain kept in double: independent of include/aar_analytic.h (no Huber)."""
+        z = np.ascontiguousarray(z, dtype=np.float64); r = np.zeros(self.num_rows)
+        self.L.aar_oracle_error_fp64_chain(self.h, _ptr(z, _dp), _ptr(r, _dp)); return r
+
     @property
     def num_vars(self): return int(self.L.aar_oracle_num_vars(self.h))
     @property
@@ -181,6 +190,13 @@ def rodrigues(r, sincos_mode=0):
     L, _ = load(); L.aar_oracle_set_sincos_mode(C.c_int(sincos_mode))
     r = np.ascontiguousarray(r, dtype=np.float64); R = np.zeros(9)
     L.aar_oracle_rodrigues(_ptr(r, _dp), _ptr(R, _dp)); return R.reshape(3, 3)
+
+
+def rodrigues_derivs(r, sincos_mode=1):
+    """dR/dr_k (3, 3, 3) of include/aar_analytic.h at the rotation vector r."""
+    L, _ = load(); L.aar_oracle_set_sincos_mode(C.c_int(sincos_mode))
+    r = np.ascontiguousarray(r, dtype=np.float64); dR = np.zeros(27)
+    L.aar_oracle_rodrigues_derivs(_ptr(r, _dp), _ptr(dR, _dp)); return dR.reshape(3, 3, 3)
 
 
 def rodrigues_inv(R):
