@@ -104,6 +104,7 @@ struct aar_problem {
     DevBuf<int2> d_pair_fc; DevBuf<double> d_pair_tab; int npairs = 0;
     DevBuf<int4> d_pair_info, d_mrun_info; DevBuf<int> d_perm_fm, d_pair_cam; DevBuf<double> d_cm_rep; int nmruns = 0;     // visiting orders of the tensor-core assembly (aar_assemble.cuh)
     bool legacy_acc = false;                                                          // AAR_ASM=legacy: round-1 lane-per-observation kernel (A/B aid)
+    bool analytic = false; DevBuf<double> d_cam_an, d_mk_an, d_fr_an;                 // analytic-Jacobian / full-FP64 variant (aar_analytic.cuh)
     DevBuf<double> d_trk_cam_inv, d_trk_Y, d_trk_z, d_trk_z0, d_trk_cost; bool trk_have_z0 = false; double track_ms = 0; long long track_runs = 0;
     DevBuf<double> d_fc, d_E, d_xinv;
     DevBuf<int> d_pair_slot_i; DevBuf<double> d_intr_tr, d_Ji;
@@ -210,7 +211,9 @@ int allreduce(aar_problem *p, double *buf, size_t n, ncclRedOp_t op) {
 int residual(aar_problem *p, const double *dz, float huber_delta, double *d_r_out) {
     LAUNCH(p, k_expand_trial, cdiv((long long)p->C + p->M + p->dp.F, 128), 128, 0, p->dp, dz);
     if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, dz, p->d_intr_tr.p);
-    if (p->dp.N > 0)
+    if (p->dp.N > 0 && p->analytic)
+        LAUNCH(p, k_residual_an, cdiv(p->dp.N, 256), 256, 0, p->dp, p->d_cam_tr.p, POSE_STRIDE, p->d_mk_tr.p, POSE_STRIDE, p->d_fr_tr.p, POSE_STRIDE, huber_delta, d_r_out, p->d_red3.p);
+    else if (p->dp.N > 0)
         LAUNCH(p, k_residual, cdiv(p->dp.N, 256), 256, 0, p->dp, p->d_cam_tr.p, POSE_STRIDE, p->d_mk_tr.p, POSE_STRIDE, p->d_fr_tr.p, POSE_STRIDE, huber_delta, d_r_out, p->d_red3.p);
     return AAR_OK;
 }
@@ -225,7 +228,8 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     const int tabs_smem = tab_bytes <= 48 * 1024;          // marker tables of the whole rig next to the per-warp pair buffers
     const size_t smem1 = (tabs_smem ? tab_bytes : 0) + PROJ_PAIR_SMEM_BYTES;
     const long long N = p->dp.N;
-    const double s1 = 1.0 / (2 * p->J_delta), s2 = s1 * s1;
+    // the staged rows hold central-difference numerators (scaled by 1 / (2 delta) once per sum) or, in the analytic variant, derivatives
+    const double s1 = p->analytic ? 1.0 : 1.0 / (2 * p->J_delta), s2 = s1 * s1;
     const int grid1 = (int)std::max<long long>(1, std::min<long long>((long long)AAR_PROJ_MINBLOCKS * p->num_sms, (N + PROJ_THREADS - 1) / PROJ_THREADS));
     prof_mark(p, 7);
     if (p->legacy_acc) {
@@ -266,7 +270,11 @@ int launch_jacobian(aar_problem *p, float huber_eval, JT *Jn) {
     CU(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem1, 1024)));
     CU(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     CU(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    LAUNCH(p, k1, grid1, PROJ_THREADS, smem1, p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, 0LL, N);
+    if (p->analytic) {
+        if constexpr (std::is_same<JT, double>::value) LAUNCH(p, k_jac_analytic, cdiv(N, 128), 128, 0, p->dp, huber_eval, Jn, p->d_Rv.p);
+        else { set_err("the analytic variant stages its rows in double"); return AAR_ERR_INVALID; }
+    } else
+        LAUNCH(p, k1, grid1, PROJ_THREADS, smem1, p->dp, huber_eval, Jn, p->d_Rv.p, tabs_smem, p->d_flag.p, 0LL, N);
     prof_mark(p, 9);
     // every warp takes an equal share of the row stream: at least ~64 rows per warp, at most the resident CTAs of the device
     const long long want = std::max<long long>(1, (N + 64LL * ASM_WARPS - 1) / (64LL * ASM_WARPS));
@@ -297,7 +305,12 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump, bool de
     const long long jobs = (long long)p->C * NVAR_CAM + (long long)p->M * NVAR_RT + (long long)p->dp.F * NVAR_RT;
     LAUNCH(p, k_expand_jac, cdiv(jobs, 128), 128, 0, p->dp, p->d_z.p, p->d_flag.p);
     if (p->opt_i) LAUNCH(p, k_expand_intr, cdiv(p->C, 64), 64, 0, p->dp, p->d_z.p, p->d_intr.p);
-    if (p->npairs > 0) LAUNCH(p, k_pair_tab, std::max(1, std::min(p->npairs, 10 * p->num_sms)), PAIR_TAB, 0, p->dp);      // 10 CTAs of 192 threads per SM: one full wave
+    if (p->analytic) LAUNCH(p, k_expand_analytic, cdiv((long long)p->C + p->M + p->dp.F, 128), 128, 0, p->dp, p->d_z.p);
+    else if (p->npairs > 0) LAUNCH(p, k_pair_tab, std::max(1, std::min(p->npairs, 10 * p->num_sms)), PAIR_TAB, 0, p->dp);      // 10 CTAs of 192 threads per SM: one full wave
+    if (Jdump && p->analytic) {
+        if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump_an, cdiv(p->dp.N, 128), 128, 0, p->dp, Jdump);
+        return AAR_OK;
+    }
     if (Jdump) {
         if (p->dp.N > 0) LAUNCH(p, k_jacobian_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, huber_eval, Jdump);
         if (p->opt_i && p->dp.N > 0) { if (p->d_Ji.n < 32 * (size_t)p->dp.N) CU(p->d_Ji.alloc(32 * (size_t)p->dp.N)); LAUNCH(p, k_intr_dump, cdiv(p->dp.N, 128), 128, 0, p->dp, p->d_Ji.p); }
@@ -305,7 +318,7 @@ int jacobian_accumulate(aar_problem *p, float huber_eval, double *Jdump, bool de
     }
     const size_t N = (size_t)p->dp.N;
     for (int attempt = 0; attempt < 2; attempt++) {
-        const bool exact = p->force_exact_staging || attempt == 1 || p->exact_next;
+        const bool exact = p->force_exact_staging || attempt == 1 || p->exact_next || p->analytic;      // the analytic variant has no float32 staging
         if (p->d_Hrr.n) CU(cudaMemsetAsync(p->d_Hrr.p, 0, p->d_Hrr.n * sizeof(double), p->stream));
         if (p->d_gr.n) CU(cudaMemsetAsync(p->d_gr.p, 0, p->d_gr.n * sizeof(double), p->stream));
         if (p->d_Hf.n) CU(cudaMemsetAsync(p->d_Hf.p, 0, p->d_Hf.n * sizeof(double), p->stream));
@@ -455,6 +468,8 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     if (p->rank < 0 || p->rank >= p->world) { set_err("bad rank"); return AAR_ERR_INVALID; }
     g_ranks_on_host = std::max(1, d->world_size);
     p->opt_i = d->optimize_cam_intrinsics != 0;
+    p->analytic = d->analytic_jacobian != 0;
+    if (p->analytic && p->opt_i) { set_err("analytic_jacobian with optimize_cam_intrinsics: the intrinsics block is built for the central-difference path only"); return AAR_ERR_UNSUPPORTED; }
     p->nrc = p->opt_c ? p->C - 1 : 0; p->nrm = p->opt_m ? p->M - 1 : 0; p->nri = p->opt_i ? 2 * p->C : 0; p->n_r = 6 * (p->nrc + p->nrm + p->nri);
     p->n_vars = p->n_r + (p->opt_f ? 6LL * p->F : 0);
     p->n_vars_ext = 6LL * (p->nrc + p->nrm) + (p->opt_f ? 6LL * p->F : 0) + (p->opt_i ? 9LL * p->C : 0);
@@ -683,7 +698,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
         }
         p->nmruns = (int)mrun_info.size();
         UP(p->d_perm_fm, perm_fm); UP(p->d_mrun_info, mrun_info);
-        { const char *e = getenv("AAR_ASM"); p->legacy_acc = e && !strcmp(e, "legacy"); }
+        { const char *e = getenv("AAR_ASM"); p->legacy_acc = e && !strcmp(e, "legacy") && !p->analytic; }
     }
 
     UP(p->d_raw_a, raw_a); UP(p->d_raw_b, raw_b); UP(p->d_obs_pair, obs_pair); UP(p->d_pair_fc, pair_fc);
@@ -693,6 +708,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
 #undef UP
     CU(p->d_und_a.alloc((size_t)Nl)); CU(p->d_und_b.alloc((size_t)Nl));
     CU(p->d_cam_tab.alloc((size_t)p->C * CAM_TAB)); CU(p->d_mk_tab.alloc((size_t)p->M * MK_TAB)); CU(p->d_fr_tab.alloc((size_t)std::max(Fl, 1) * FR_TAB));
+    if (p->analytic) { CU(p->d_cam_an.alloc((size_t)p->C * CAM_AN)); CU(p->d_mk_an.alloc((size_t)p->M * RT_AN)); CU(p->d_fr_an.alloc((size_t)std::max(Fl, 1) * RT_AN)); }
     CU(p->d_cam_tr.alloc((size_t)p->C * POSE_STRIDE)); CU(p->d_mk_tr.alloc((size_t)p->M * POSE_STRIDE)); CU(p->d_fr_tr.alloc((size_t)std::max(Fl, 1) * POSE_STRIDE));
     const size_t nz = (size_t)std::max<long long>(p->n_vars, 1);
     CU(p->d_z.alloc(nz)); CU(p->d_zt.alloc(nz)); CU(p->d_z0.alloc(nz));
@@ -721,6 +737,7 @@ static int create_impl(const aar_problem_desc *d, aar_problem **out, bool host_o
     dp.frame_cs_cum = p->d_frame_cs_cum.p;
     dp.cam_tab = p->d_cam_tab.p; dp.mk_tab = p->d_mk_tab.p; dp.fr_tab = p->d_fr_tab.p; dp.cam_tr = p->d_cam_tr.p; dp.mk_tr = p->d_mk_tr.p; dp.fr_tr = p->d_fr_tr.p;
     dp.cam_fixed = p->d_cam_fixed.p; dp.mk_fixed = p->d_mk_fixed.p; dp.fr_fixed = p->d_fr_fixed.p;
+    dp.analytic = p->analytic ? 1 : 0; dp.cam_an = p->d_cam_an.p; dp.mk_an = p->d_mk_an.p; dp.fr_an = p->d_fr_an.p;
 
     // ---- remove_distortions (multicam_mapper.cpp:554-578) on the device: raw -> und.
     // raw_a/raw_b hold corners (0,1) / (2,3); run the point kernel on each half.
@@ -1156,7 +1173,7 @@ int aar_lm_iterate(aar_problem *p, int32_t max_iters, aar_lm_report *rep) {
     if (rep) { rep->trace_len = 0; rep->initial_cost = p->initial_cost; }
     double *S = p->d_red.p, *b = S + (size_t)n_r * n_r, *Br = b + n_r;
     const char *no_graph = getenv("AAR_NO_GRAPH");           // development aid: host-driven loop only
-    const bool graph_eligible = (!p->comm || p->peer_ok) && !p->profiling && !P.verbose && !p->legacy_acc && !p->force_exact_staging && !(no_graph && *no_graph == '1') && p->dp.N > 0;
+    const bool graph_eligible = (!p->comm || p->peer_ok) && !p->profiling && !P.verbose && !p->legacy_acc && !p->force_exact_staging && !p->analytic && !(no_graph && *no_graph == '1') && p->dp.N > 0;
     for (int it = 0; it < max_iters && !mustExit; it++) {
         if (graph_eligible && p->h_st->mu >= 0 && (p->lm_graph_ok || !p->lm_graph_tried)) {
             // every iteration but the first of a solve: inside the graph, without the host (see lm_graph_build)

@@ -58,6 +58,9 @@ struct DevProblem {
     double *cam_tab, *mk_tab, *fr_tab;
     double *cam_tr, *mk_tr, *fr_tr; // trial (z + delta) tables, base only: [.][12]
     const double *cam_fixed, *mk_fixed, *fr_fixed; // host matrices [.][12] for non-optimised groups
+    // analytic-Jacobian / full-FP64 variant (aar_analytic.cuh): rotation derivatives of every optimised camera / marker / frame at z
+    int analytic;
+    double *cam_an, *mk_an, *fr_an;
 };
 
 __device__ __forceinline__ int obs_cam(int cm) { return cm & 0xfff; }
@@ -148,6 +151,7 @@ __device__ __forceinline__ void load8(const float4 *a, const float4 *b, long lon
 #include "aar_jacobian.cuh"
 #include "aar_assemble.cuh"
 #include "aar_intrinsics.cuh"
+#include "aar_analytic.cuh"
 
 namespace aar {
 

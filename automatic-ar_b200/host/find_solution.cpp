@@ -1,11 +1,11 @@
 // find_solution — the reference's app (/root/reference/apps/find_solution.cpp:28-181) on the CUDA path, OpenCV-free:
 //   find_solution <path_to_data_folder> <marker_size> [-subseqs] [-exclude-cams <cam_id> ...] [-with-huber] [-thresh <t>]
-//                 [-consensus-max <k>] [-init <initial.solution>]
+//                 [-consensus-max <k>] [-init <initial.solution>] [-analytic]
 // Reads <folder>/<cam>/calib.yml and <folder>/aruco.detections, builds the starting point with the Initializer (device: IPPE per
 // detection + consensus; include/aar_init.h), writes initial<suffix>.solution(.yaml), solves on the GPU (include/aar_cuda.h) and
 // writes final<suffix>.solution(.yaml) — the file names of find_solution.cpp:76-100.  Two additions: -consensus-max (SURVEY 8(f) row 3,
 // the reference's exhaustive consensus is O(n^2) in the number of co-observations) and -init (start from an existing .solution
-// instead of the detections).  Unlike the reference (whose option loop starts at argv[4]) options are read from argv[3] on.
+// instead of the detections) and -analytic (analytic Jacobian, residuals in double: include/aar_analytic.h; not the reference's arithmetic).  Unlike the reference (whose option loop starts at argv[4]) options are read from argv[3] on.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,12 +17,12 @@
 
 int main(int argc, char **argv) {
     if (argc < 3) {
-        std::cout << "Usage: find_solution <path_to_data_folder> <marker_size> [-subseqs] [-exclude-cams <cam_id> ...] [-with-huber] [-thresh <t>] [-consensus-max <k>] [-init <file>]" << std::endl;
+        std::cout << "Usage: find_solution <path_to_data_folder> <marker_size> [-subseqs] [-exclude-cams <cam_id> ...] [-with-huber] [-thresh <t>] [-consensus-max <k>] [-init <file>] [-analytic]" << std::endl;
         return -1;
     }
     const std::string folder = argv[1];
     const double marker_size = std::stod(argv[2]);
-    bool use_subseqs = false, with_huber = false, set_threshold = false; double threshold = 2.0; int consensus_max = 0;
+    bool use_subseqs = false, with_huber = false, set_threshold = false, analytic = false; double threshold = 2.0; int consensus_max = 0;
     std::set<int> excluded_cams; std::string init_path;
     enum { NONE, EXCLUDE, THRESH, CMAX, INIT } flag = NONE;
     for (int i = 3; i < argc; i++) {
@@ -30,6 +30,7 @@ int main(int argc, char **argv) {
         if (a == "-subseqs") { use_subseqs = true; flag = NONE; }
         else if (a == "-exclude-cams") flag = EXCLUDE;
         else if (a == "-with-huber") { with_huber = true; flag = NONE; }
+        else if (a == "-analytic") { analytic = true; flag = NONE; }
         else if (a == "-thresh") { set_threshold = true; flag = THRESH; }
         else if (a == "-consensus-max") flag = CMAX;
         else if (a == "-init") flag = INIT;
@@ -74,6 +75,7 @@ int main(int argc, char **argv) {
         mcm.set_optmize_flag_cam_poses(true); mcm.set_optmize_flag_marker_poses(true); mcm.set_optmize_flag_object_poses(true);
         mcm.set_optmize_flag_cam_intrinsics(false);              // find_solution.cpp:140
         if (with_huber) mcm.set_with_huber(true);
+        if (analytic) mcm.set_analytic_jacobian(true);
         auto start = std::chrono::system_clock::now();
         mcm.solve();
         d += std::chrono::system_clock::now() - start;

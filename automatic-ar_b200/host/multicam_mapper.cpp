@@ -165,7 +165,7 @@ void MultiCamMapper::make_handle(bool undist) {
     d.cam_T = Tc.data(); d.marker_T = Tm.data(); d.frame_T = To.data(); d.cam_K = K.data(); d.cam_dist = D.data();
     d.num_detections = (int64_t)df.size(); d.det_frame = df.data(); d.det_cam = dc.data(); d.det_marker = dm.data(); d.det_xy = xy.data();
     d.optimize_cam_poses = config.optimize_cam_poses; d.optimize_marker_poses = config.optimize_marker_poses; d.optimize_object_poses = config.optimize_object_poses;
-    d.optimize_cam_intrinsics = config.optimize_cam_intrinsics; d.with_huber = with_huber; d.corners_undistorted = undist;
+    d.optimize_cam_intrinsics = config.optimize_cam_intrinsics; d.with_huber = with_huber; d.corners_undistorted = undist; d.analytic_jacobian = analytic_jacobian;
     d.J_delta = 1e-3; d.device = 0; d.world_size = 1;
     check(aar_problem_create(&d, &handle), "aar_problem_create");
 }

@@ -49,6 +49,8 @@ public:
     void set_optmize_flag_object_poses(bool v) { config.optimize_object_poses = v; drop_handle(); }
     void set_optmize_flag_cam_intrinsics(bool v) { config.optimize_cam_intrinsics = v; drop_handle(); }
     void set_with_huber(bool v) { with_huber = v; drop_handle(); }
+    // not in the reference: analytic Jacobian + residuals kept in double (include/aar_analytic.h); pose blocks only
+    void set_analytic_jacobian(bool v) { analytic_jacobian = v; drop_handle(); }
     void set_config(const Config &c) { config = c; drop_handle(); }
     size_t get_num_vars(const Config &conf) const;
 
@@ -86,7 +88,7 @@ private:
     void check(int rc, const char *what) const;
 
     Config config;
-    bool with_huber = false, corners_undistorted = false;
+    bool with_huber = false, corners_undistorted = false, analytic_jacobian = false;
     size_t root_cam = 0, root_marker = 0;
     double marker_size = 0;
     aar_problem *handle = nullptr;

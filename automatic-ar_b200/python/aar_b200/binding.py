@@ -54,7 +54,7 @@ class Desc(C.Structure):
                 ("cam_T", C.c_void_p), ("marker_T", C.c_void_p), ("frame_T", C.c_void_p), ("cam_K", C.c_void_p), ("cam_dist", C.c_void_p),
                 ("num_detections", C.c_int64), ("det_frame", C.c_void_p), ("det_cam", C.c_void_p), ("det_marker", C.c_void_p), ("det_xy", C.c_void_p),
                 ("optimize_cam_poses", C.c_uint8), ("optimize_marker_poses", C.c_uint8), ("optimize_object_poses", C.c_uint8),
-                ("optimize_cam_intrinsics", C.c_uint8), ("with_huber", C.c_uint8), ("corners_undistorted", C.c_uint8), ("reserved", C.c_uint8 * 2),
+                ("optimize_cam_intrinsics", C.c_uint8), ("with_huber", C.c_uint8), ("corners_undistorted", C.c_uint8), ("analytic_jacobian", C.c_uint8), ("reserved", C.c_uint8 * 1),
                 ("J_delta", C.c_double), ("device", C.c_int32), ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32)]
 
 
@@ -122,7 +122,7 @@ class Problem:
         return dict(frame_idx=of, cam_idx=oc, marker_idx=om, has_jac=oj)
 
     @staticmethod
-    def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics=False):
+    def _desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics=False, analytic=False):
         k = {}
         k["cam_ids"] = np.ascontiguousarray(rig.cam_ids, np.int32); k["marker_ids"] = np.ascontiguousarray(rig.marker_ids, np.int32)
         k["frame_ids"] = np.ascontiguousarray(rig.frame_ids, np.int32)
@@ -141,14 +141,15 @@ class Problem:
         d.det_frame, d.det_cam, d.det_marker, d.det_xy = _vp(k["det_frame"]), _vp(k["det_cam"]), _vp(k["det_marker"]), _vp(k["det_xy"])
         d.optimize_cam_poses, d.optimize_marker_poses, d.optimize_object_poses, d.optimize_cam_intrinsics = int(cams), int(markers), int(objects), int(intrinsics)
         d.with_huber = int(with_huber); d.J_delta = J_delta; d.device = device
+        d.analytic_jacobian = int(analytic)
         d.stream = C.c_void_p(stream) if stream else None
         d.rank, d.world_size = rank, world_size
         return d, k
 
     def __init__(self, rig, use_init=True, cams=True, markers=True, objects=True, with_huber=False, device=0, stream=None,
-                 rank=0, world_size=1, J_delta=0.0, intrinsics=False):
+                 rank=0, world_size=1, J_delta=0.0, intrinsics=False, analytic=False):
         L = lib()
-        d, self._keep = self._desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics)
+        d, self._keep = self._desc(rig, use_init, cams, markers, objects, with_huber, device, stream, rank, world_size, J_delta, intrinsics, analytic)
         self.h = C.c_void_p()
         _chk(L.aar_problem_create(C.byref(d), C.byref(self.h)), "aar_problem_create")
         self.nC, self.nM, self.nF = d.num_cams, d.num_markers, d.num_frames

@@ -57,7 +57,10 @@ typedef struct {
     uint8_t with_huber;
     uint8_t corners_undistorted;                      /* detections come from a .solution file (already undistorted, multicam_mapper.cpp:1085-1088):
                                                        * no remove_distortions pass, and the Jacobian's "raw" corners are these corners too */
-    uint8_t reserved[2];
+    uint8_t analytic_jacobian;                        /* 0: the reference's central differences on float32-rounded projections (parity path).
+                                                       * 1: analytic Jacobian, residuals kept in double (include/aar_analytic.h) — NOT the reference's
+                                                       *    arithmetic; pose blocks only (with optimize_cam_intrinsics: AAR_ERR_UNSUPPORTED); track ignores it */
+    uint8_t reserved[1];
     double J_delta;                                   /* multicam_mapper.h:189, 0 -> 1e-3 */
     /* placement */
     int32_t device;                                   /* CUDA device ordinal */
