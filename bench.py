@@ -38,6 +38,7 @@ RESTART = 10            # LM iterations between restarts from z0
 W_J_FLOP = 9.0e3        # algorithmic FP64 flop per marker observation per Jacobian evaluation
 W_PROJ_FLOP = 5912.0    # ... of which in k_jac_project: 37 projections x 152 + 288 for the central differences
 W_ASM_FLOP = 3040.0     # ... and in the assembly kernels: 2 736 (upper J^T J blocks) + 304 (J^T r, cost)
+W_AN_FLOP = 1700.0      # the analytic variant's k_jac_analytic (--analytic): 3 chained rigid transforms, one division, 18 directional derivatives per corner
 OBS_BYTES = 76          # HBM bytes per marker observation read by k_jac_project (2 x 8 float corners + 12 B indices; the pair table adds 1536 B per (frame, camera) pair)
 STAGE_BYTES = 640       # HBM bytes per marker observation written by k_jac_project (144 float numerators + 8 double residuals)
 CPU_SAMPLE_FRAMES = 300
@@ -315,7 +316,7 @@ def run_track(args, rank, world, local_rank):
                              "traffic": None},
                 "setup_s": {"generate": t_gen, "create_upload_undistort": t_create}}
         line["roofline"]["hbm"]["frac"] = line["roofline"]["hbm"]["achieved"] / peaks["hbm_gbs"]
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.analytic:
             r = track_cpu_run(TRACK_CPU_FRAMES, check_device=local_rank)
             line["cpu_baseline"] = {"value": r["work"] / r["seconds"], "unit": "corner-observations/s", "frames_per_s": r["frames"] / r["seconds"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
             line["parity_check"] = r["parity_check"]
@@ -344,7 +345,7 @@ def run_ours(args, rank, world, local_rank):
     t_gen = time.time() - t0
     stream = torch.cuda.Stream()
     t0 = time.time()
-    p = binding.Problem(rig, device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world)
+    p = binding.Problem(rig, device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world, analytic=args.analytic)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -478,7 +479,12 @@ def run_ours(args, rank, world, local_rank):
                     "traffic": t, "traffic_over_algorithmic": (t / bytes_alg if (t and bytes_alg) else None),
                     "dram_gbs_at_traffic": (t / (ms_launch * 1e-3) / 1e9 if (t and ms_launch > 0) else None),
                     "dram_frac_of_peak_at_traffic": (t / (ms_launch * 1e-3) / 1e9 / peaks["hbm_gbs"] if (t and ms_launch > 0) else None)}
+        if args.analytic:        # not the headline: the analytic-Jacobian / full-FP64 variant (include/aar_analytic.h), rows staged in double
+            kernels_an = entry("k_jac_analytic", jac_ms, W_AN_FLOP * n_local, OBS_BYTES * n_local,
+                               "analytic 8 x 18 Jacobian block + residual of every marker observation in double (about 1.7 kflop: 3 chained rigid transforms, one division and 18 "
+                               "directional derivatives per corner); writes 1280-byte rows — bound by the HBM writes, not by FP64", None)
         kernels = [
+            kernels_an if args.analytic else
             entry("k_jac_project", jac_ms, W_PROJ_FLOP * n_local, OBS_BYTES * n_local,
                   "37 pinhole projections per marker observation (residual + quantised central-difference numerators); the reference's a*b+c are two IEEE operations "
                   "(-fmad=false, bit-exact parity), so the attainable peak of this kernel is the non-FMA issue rate = half the DFMA peak", "k_jac_project"),
@@ -488,7 +494,7 @@ def run_ours(args, rank, world, local_rank):
             entry("k_schur_syrk", syrk_ms, syrk_flop, 0.0, "S -= E E^T over the frames of this rank (upper triangle), FP64 tensor cores; launched once per LM try", "k_schur_syrk"),
         ]
         dom = max(kernels, key=lambda e: e["share_of_step"])
-        flop_step = (W_J_FLOP * n_local + 152.0 * n_local * tries_total / K + syrk_flop * tries_total / K)
+        flop_step = ((W_AN_FLOP + W_ASM_FLOP if args.analytic else W_J_FLOP) * n_local + 152.0 * n_local * tries_total / K + syrk_flop * tries_total / K)
         step_ach = flop_step / (ms / K * 1e-3) / 1e12
         line = {
             "metric": "corner_obs_per_s", "value": value, "unit": "corner-observations/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -501,6 +507,8 @@ def run_ours(args, rank, world, local_rank):
                                       else ("ncclAllReduce per LM try" if world > 1 else "none")),
                        "l2": ("per-step working set %.0f MB per rank (observations + staged Jacobian block, streamed once per step) %s the 126 MB L2; no explicit flush"
                               % ((OBS_BYTES + 2 * STAGE_BYTES) * n_local / 1e6, "exceeds" if (OBS_BYTES + 2 * STAGE_BYTES) * n_local > 2 * 126e6 else "does NOT exceed")),
+                       "jacobian": ("analytic, residuals in double (aar_problem_desc::analytic_jacobian = 1; NOT the reference's arithmetic)" if args.analytic
+                                    else "the reference's central differences on float32-rounded projections (bit-exact parity path)"),
                        "restart_every": RESTART, "step": "one SparseLevMarq::step (J + JtJ + Schur + solve + trial residual)"},
             "e2e": {"value": corner * K / (ms_e2e * 1e-3), "unit": "corner-observations/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(8 * n_vars * calls / K), "d2h_bytes_per_step": int((8 * n_vars * calls + 96 * e2e_tries) / K),
@@ -542,6 +550,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-track", action="store_true")
+    ap.add_argument("--analytic", action="store_true", help="analytic-Jacobian / full-FP64 variant instead of the parity path (no cpu_baseline / parity_check legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

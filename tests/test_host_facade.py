@@ -113,6 +113,24 @@ def test_find_solution_app_matches_binding(host_bins, tmp_path):
 
 
 @pytest.mark.gpu
+def test_find_solution_app_analytic_option(host_bins, tmp_path):
+    """find_solution -analytic: MultiCamMapper::set_analytic_jacobian through the facade (include/aar_analytic.h) gives the solve of the
+    binding's analytic variant (no float32 quantisation in this variant: the two agree far inside the faithful path's envelope)."""
+    from aar_b200 import binding
+    rig = synth.make_config("cfg1")
+    synth.write_solution_file(str(tmp_path / "initial.solution"), rig)
+    out = subprocess.run([os.path.join(host_bins, "find_solution"), str(tmp_path), "0.05", "-init", str(tmp_path / "initial.solution"), "-analytic"], check=True, capture_output=True, text=True).stdout
+    app_cost = float(out.split("final_error:")[1].split()[0])
+    p = binding.Problem(rig, analytic=True)
+    z, fc, it, tr = p.solve(p.mats2evec())
+    assert int(out.split("iterations:")[1].split()[0]) == it
+    assert abs(app_cost - fc) <= 1e-9 * fc
+    pf = binding.Problem(rig)
+    _, fc_f, _, _ = pf.solve(pf.mats2evec())
+    assert app_cost != fc_f and abs(app_cost - fc_f) <= 1e-4 * fc_f       # it really is the other variant, next to the same optimum
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("workload", ["cfg1", "distorted"])
 def test_find_solution_from_detections_and_calib(host_bins, oracle_mod, tmp_path, workload):
     """apps/find_solution.cpp:102-177 end to end: <cam>/calib.yml + aruco.detections -> Initializer -> MultiCamMapper::solve ->
