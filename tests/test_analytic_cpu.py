@@ -82,6 +82,25 @@ def test_analytic_jacobian_against_central_differences_of_the_independent_chain(
     assert 1e-12 < rel < 5e-3, rel
 
 
+def test_analytic_jacobian_on_a_planar_board(oracle_mod):
+    """All markers coplanar and aligned with the root marker (a printed board): their rotation vectors are exactly zero, which is the
+    small-angle branch of the Rodrigues derivatives inside a full Jacobian; one camera pose is the identity rotation as well."""
+    rig = synth.make_rig(3, 5, 10, 6, seed=33)
+    for T in (rig.T_marker_init, rig.T_marker_true):
+        T[:, :3, :3] = np.eye(3)
+    rig.T_cam_init[1, :3, :3] = np.eye(3)
+    o = oracle_mod.Oracle(rig); o.set_analytic(True)
+    z = o.mats2evec()
+    assert np.count_nonzero(z[6 * 2:6 * 2 + 6 * 4].reshape(-1, 6)[:, :3]) == 0 and not z[0:3].any()      # marker blocks and camera 1: r = 0
+    rows, n = o.num_rows, o.num_vars
+    J = _csc_to_dense(*o.jacobian(z), rows)
+    Jfd = np.zeros((rows, n)); h = 1e-6
+    for c in range(n):
+        d = np.zeros(n); d[c] = h
+        Jfd[:, c] = (o.error_fp64_chain(z + d) - o.error_fp64_chain(z - d)) / (2 * h)
+    assert np.abs(J - Jfd).max() / np.abs(Jfd).max() < 5e-8
+
+
 def test_analytic_solve_reaches_the_faithful_optimum(oracle_mod):
     """The two variants minimise (nearly) the same function: from the same start the reference solver, driven by the analytic
     functions, ends within the noise floor of the faithful solve."""
