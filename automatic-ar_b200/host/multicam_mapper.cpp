@@ -392,4 +392,89 @@ std::vector<int> MultiCamMapper::read_subseqs(const std::string &path) {
     return v;
 }
 
+// cv::Mat::inv() of a 4x4 (DECOMP_LU: Gaussian elimination with partial pivoting on [A | I], OpenCV's hal::LU operation order)
+static Mat44 inv44_lu(const Mat44 &in) {
+    double A[16], b[16];
+    std::memcpy(A, in.m, sizeof A);
+    for (int i = 0; i < 16; i++) b[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 4; i++) {
+        int k = i;
+        for (int j = i + 1; j < 4; j++) if (std::fabs(A[j * 4 + i]) > std::fabs(A[k * 4 + i])) k = j;
+        if (std::fabs(A[k * 4 + i]) < 2.2204460492503131e-16 * 100) { Mat44 z; std::memset(z.m, 0, sizeof z.m); return z; }      // singular: cv::Mat::inv() returns zeros
+        if (k != i) { for (int j = i; j < 4; j++) std::swap(A[i * 4 + j], A[k * 4 + j]); for (int j = 0; j < 4; j++) std::swap(b[i * 4 + j], b[k * 4 + j]); }
+        const double d = -1 / A[i * 4 + i];
+        for (int j = i + 1; j < 4; j++) {
+            const double alpha = A[j * 4 + i] * d;
+            for (int kk = i + 1; kk < 4; kk++) A[j * 4 + kk] += alpha * A[i * 4 + kk];
+            for (int kk = 0; kk < 4; kk++) b[j * 4 + kk] += alpha * b[i * 4 + kk];
+        }
+    }
+    for (int i = 3; i >= 0; i--)
+        for (int j = 0; j < 4; j++) {
+            double sum = b[i * 4 + j];
+            for (int k = i + 1; k < 4; k++) sum -= A[i * 4 + k] * b[k * 4 + j];
+            b[i * 4 + j] = sum / A[i * 4 + i];
+        }
+    Mat44 R; std::memcpy(R.m, b, sizeof b); return R;
+}
+
+// multicam_mapper.cpp:86-117: size_t n1, n1 x { int node1, size_t n2, n2 x { int node2, double r[3], double t[3] } }, int root_cam_id.
+// Every stored edge also yields its inverse (transforms[node2][node1] = T.inv(), :111).
+int MultiCamMapper::read_stereo_calib(const std::string &path, std::map<int, std::map<int, Mat44>> &transforms) {
+    std::ifstream f(path, std::ios_base::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open stereo calib file to read at: " + path);
+    size_t n1 = 0; rd(f, n1);
+    for (size_t i = 0; i < n1; i++) {
+        int node1 = 0; size_t n2 = 0; rd(f, node1); rd(f, n2);
+        for (size_t j = 0; j < n2; j++) {
+            int node2 = 0; double v[6] = {0, 0, 0, 0, 0, 0};
+            rd(f, node2);
+            for (int k = 0; k < 6; k++) rd(f, v[k]);
+            const Mat44 T = vec62mat(v);
+            transforms[node1][node2] = T;
+            transforms[node2][node1] = inv44_lu(T);
+        }
+    }
+    int root_cam_id = 0; rd(f, root_cam_id);
+    return root_cam_id;
+}
+
+void MultiCamMapper::write_stereo_calib(const std::string &path, const std::map<int, std::map<int, Mat44>> &transforms, int root_cam_id) {      // :119-143
+    std::ofstream f(path, std::ios_base::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open stereo calib file to write at: " + path);
+    const size_t n1 = transforms.size(); wr(f, n1);
+    for (auto &a : transforms) {
+        wr(f, a.first);
+        const size_t n2 = a.second.size(); wr(f, n2);
+        for (auto &b : a.second) {
+            wr(f, b.first);
+            double v[6]; mat2vec6(b.second, v);
+            for (int k = 0; k < 6; k++) wr(f, v[k]);
+        }
+    }
+    wr(f, root_cam_id);
+}
+
+// multicam_mapper.cpp:145-168: repeated { size_t frame_num, double r[3], double t[3] } until EOF; a record cut short throws
+void MultiCamMapper::read_ground_truth(const std::string &path, std::map<size_t, Mat44> &poses) {
+    std::ifstream f(path, std::ios_base::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open ground truth file to read at: " + path);
+    size_t frame_num = 0;
+    while (rd(f, frame_num)) {
+        double v[6];
+        for (int k = 0; k < 6; k++) if (!rd(f, v[k])) throw std::runtime_error("Unexpected end of input ground truth file : " + path);
+        poses[frame_num] = vec62mat(v);
+    }
+}
+
+void MultiCamMapper::write_ground_truth(const std::string &path, const std::map<size_t, Mat44> &poses) {      // :170-184
+    std::ofstream f(path, std::ios_base::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open ground truth file to write at: " + path);
+    for (auto &p : poses) {
+        const size_t frame_num = p.first; wr(f, frame_num);
+        double v[6]; mat2vec6(p.second, v);
+        for (int k = 0; k < 6; k++) wr(f, v[k]);
+    }
+}
+
 } // namespace aar

@@ -1,7 +1,7 @@
 // multicam_mapper.h — host-side mirror of the reference's MultiCamMapper (/root/reference/libs/multicam_mapper.h:14-83)
 // for the joint-optimisation path: same method names, argument meaning and file formats, cv::Mat replaced by
 // aar::Mat44, the optimisation itself forwarded to the CUDA path through the C ABI of include/aar_cuda.h.
-// What is NOT here: overlays / visualisation (GUI), stereo-calib and ground-truth files.
+// What is NOT here: overlays / visualisation (GUI).
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -63,6 +63,11 @@ public:
     static void write_detections_file(const std::string &path, const std::vector<std::vector<std::vector<Marker>>> &seq);      // :216-237
     static std::vector<std::vector<std::vector<Marker>>> read_detections_file(const std::string &path, const std::vector<int> &subseqs = std::vector<int>());   // initializer.cpp:316-362
     static std::vector<int> read_subseqs(const std::string &path);                                                            // :46-55
+    // pairwise camera transforms and per-frame ground-truth poses as (rotation vector, translation) records (:86-184)
+    static int read_stereo_calib(const std::string &path, std::map<int, std::map<int, Mat44>> &transforms);                    // returns the root camera id
+    static void write_stereo_calib(const std::string &path, const std::map<int, std::map<int, Mat44>> &transforms, int root_cam_id);
+    static void read_ground_truth(const std::string &path, std::map<size_t, Mat44> &poses);
+    static void write_ground_truth(const std::string &path, const std::map<size_t, Mat44> &poses);
 
     size_t get_root_cam() const { return root_cam; }
     size_t get_root_marker() const { return root_marker; }

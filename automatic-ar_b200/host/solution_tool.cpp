@@ -1,6 +1,8 @@
 // solution_tool — format round trips for the tests (no GPU needed):
 //   solution_tool roundtrip <in.solution> <out.solution> [<out.yaml>]     read + write back (must be byte identical)
 //   solution_tool detections <in.detections> <out.detections>             read + write back
+//   solution_tool stereo <in.stereo_calib> <out.stereo_calib>             read + write back; prints root id and every 4x4 (incl. the inverses read_stereo_calib adds)
+//   solution_tool truth <in.ground_truth> <out.ground_truth>              read + write back; prints every pose
 //   solution_tool calib <data_folder> -                                   CamConfig::read_cam_configs: one line per camera, %.17g
 //   solution_tool resolve_full <in.solution> <out.solution>               (GPU) the same with the default Config (camera intrinsics optimised too)
 //   solution_tool resolve <in.solution> <out.solution>                    (GPU) re-create the mapper through the 8-argument
@@ -22,6 +24,17 @@ int main(int argc, char **argv) {
             auto d = aar::MultiCamMapper::read_detections_file(argv[2]);
             aar::MultiCamMapper::write_detections_file(argv[3], d);
             std::cout << d.size() << " frames" << std::endl;
+        } else if (mode == "stereo") {
+            std::map<int, std::map<int, aar::Mat44>> tr;
+            const int root = aar::MultiCamMapper::read_stereo_calib(argv[2], tr);
+            std::printf("root %d\n", root);
+            for (auto &a : tr) for (auto &b : a.second) { std::printf("%d %d", a.first, b.first); for (int i = 0; i < 16; i++) std::printf(" %.17g", b.second.m[i]); std::printf("\n"); }
+            aar::MultiCamMapper::write_stereo_calib(argv[3], tr, root);
+        } else if (mode == "truth") {
+            std::map<size_t, aar::Mat44> poses;
+            aar::MultiCamMapper::read_ground_truth(argv[2], poses);
+            for (auto &p : poses) { std::printf("%zu", p.first); for (int i = 0; i < 16; i++) std::printf(" %.17g", p.second.m[i]); std::printf("\n"); }
+            aar::MultiCamMapper::write_ground_truth(argv[3], poses);
         } else if (mode == "calib") {
             const std::vector<aar::CamConfig> cc = aar::CamConfig::read_cam_configs(argv[2]);
             for (const aar::CamConfig &c : cc) {

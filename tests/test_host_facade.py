@@ -60,6 +60,64 @@ def test_detections_file_round_trip(host_bins, tmp_path):
     assert int(out.split()[0]) == int(rig.frame_ids.max())            # one frame fewer than written (ids 0..max)
 
 
+def test_stereo_calib_and_ground_truth_files(host_bins, tmp_path):
+    """read/write_stereo_calib and read/write_ground_truth (multicam_mapper.cpp:86-184): records of (rotation vector, translation) as
+    the reference lays them out; matrices against cv2.Rodrigues, the added inverse edges against cv2.invert (cv::Mat::inv, LU)."""
+    import struct
+    import cv2
+    rng = np.random.default_rng(12)
+    edges = {0: {1: rng.normal(0, 0.7, 6), 2: rng.normal(0, 0.7, 6)}, 5: {3: rng.normal(0, 0.7, 6)}}
+    a, b = str(tmp_path / "stereo.calib"), str(tmp_path / "stereo2.calib")
+    with open(a, "wb") as fh:
+        fh.write(struct.pack("<Q", len(edges)))
+        for n1, sec in edges.items():
+            fh.write(struct.pack("<iQ", n1, len(sec)))
+            for n2, v in sec.items():
+                fh.write(struct.pack("<i6d", n2, *v))
+        fh.write(struct.pack("<i", 5))
+    out = subprocess.run([os.path.join(host_bins, "solution_tool"), "stereo", a, b], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert out[0] == "root 5"
+    got = {(int(l.split()[0]), int(l.split()[1])): np.array([float(x) for x in l.split()[2:]]).reshape(4, 4) for l in out[1:]}
+    assert set(got) == {(0, 1), (1, 0), (0, 2), (2, 0), (5, 3), (3, 5)}
+    for n1, sec in edges.items():
+        for n2, v in sec.items():
+            T = np.eye(4); T[:3, :3] = cv2.Rodrigues(v[:3].reshape(3, 1))[0]; T[:3, 3] = v[3:]
+            assert np.abs(got[(n1, n2)] - T).max() <= 2.3e-16                  # shared sincos: within one ulp of libm's (tests/test_oracle_pin.py)
+            assert np.abs(got[(n2, n1)] - cv2.invert(got[(n1, n2)])[1]).max() <= 1e-15
+    # written back: same structure, every stored edge and its inverse, ids ascending like std::map; vectors to R -> r accuracy
+    raw = open(b, "rb").read()
+    (n1,) = struct.unpack_from("<Q", raw, 0); off = 8; seen = {}
+    for _ in range(n1):
+        node1, n2 = struct.unpack_from("<iQ", raw, off); off += 12
+        for _ in range(n2):
+            rec = struct.unpack_from("<i6d", raw, off); off += 52
+            seen[(node1, rec[0])] = np.array(rec[1:])
+    assert struct.unpack_from("<i", raw, off)[0] == 5 and off + 4 == len(raw)
+    assert list(seen) == sorted(seen) and set(seen) == set(got)
+    for (n1_, n2_), v in seen.items():
+        assert np.abs(cv2.Rodrigues(v[:3].reshape(3, 1))[0] - got[(n1_, n2_)][:3, :3]).max() <= 1e-12 and np.array_equal(v[3:], got[(n1_, n2_)][:3, 3])
+    # ground truth: frame number + pose records until EOF; a record cut short is an error like in the reference
+    poses = {3: rng.normal(0, 0.5, 6), 11: rng.normal(0, 0.5, 6), 4: rng.normal(0, 0.5, 6)}
+    g, g2 = str(tmp_path / "truth.bin"), str(tmp_path / "truth2.bin")
+    with open(g, "wb") as fh:
+        for f, v in poses.items():
+            fh.write(struct.pack("<Q6d", f, *v))
+    out = subprocess.run([os.path.join(host_bins, "solution_tool"), "truth", g, g2], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert [int(l.split()[0]) for l in out] == [3, 4, 11]
+    for l in out:
+        f = int(l.split()[0]); T = np.array([float(x) for x in l.split()[1:]]).reshape(4, 4); v = poses[f]
+        assert np.abs(T[:3, :3] - cv2.Rodrigues(v[:3].reshape(3, 1))[0]).max() <= 2.3e-16 and np.array_equal(T[:3, 3], v[3:]) and np.array_equal(T[3], [0, 0, 0, 1])
+    raw2 = open(g2, "rb").read()
+    assert len(raw2) == 3 * 56
+    for i, f in enumerate([3, 4, 11]):
+        rec = struct.unpack_from("<Q6d", raw2, 56 * i)
+        assert rec[0] == f and np.abs(np.array(rec[1:]) - poses[f]).max() <= 1e-12
+    cut = open(g, "rb").read()[:-10]
+    open(g, "wb").write(cut)
+    r = subprocess.run([os.path.join(host_bins, "solution_tool"), "truth", g, g2], capture_output=True, text=True)
+    assert r.returncode == 2 and "Unexpected end of input ground truth file" in r.stderr
+
+
 def test_calib_reader_on_cv2_written_files(host_bins, tmp_path):
     """CamConfig::read_cam_configs (libs/cam_config.cpp:52-95) on calib.yml files written by OpenCV's own cv::FileStorage (cv2 4.13),
     the writer the reference's datasets come from: every value must come back exactly; folders are taken in numeric order."""
